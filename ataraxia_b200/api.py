@@ -1,0 +1,423 @@
+"""Host-side mirror of the reference's Engine API for the hot path, over the C-ABI.
+
+Same class names, method names, argument meaning and quirks as
+/root/reference/Engine/include/{Scene,SceneNode,Camera,Renderer}.h, so the parity tests read
+like reference client code (Engine/src/main.cpp:211-220):
+
+    renderer.onResize(w, h); camera.Resize(w, h); renderer.Render(camera, scene)
+
+All arithmetic that parity depends on (matrices, flattening) runs inside the native library
+(atx_host_* helpers); all rendering runs in the CUDA kernels. Nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import LIGHT_DTYPE, MATERIAL_DTYPE, SPHERE_DTYPE, check, f32, fptr, vptr
+
+IDENTITY = np.eye(4, dtype=np.float32).reshape(-1)  # column-major == row-major for I
+
+
+def _vec3(v) -> np.ndarray:
+    return np.asarray(v, dtype=np.float32).reshape(3).copy()
+
+
+@dataclass
+class Sphere:
+    """SceneNode.h:11-21."""
+    center: Sequence[float] = (0.0, 0.0, 0.0)
+    radius: float = 0.0
+    id: int = 0  # material index
+
+
+@dataclass
+class Material:
+    """Scene.h:28-47 (defaults included)."""
+    albedo: Sequence[float] = (1.0, 1.0, 1.0)
+    roughness: float = 0.0
+    metallic: float = 0.0
+    F0: Sequence[float] = (0.04, 0.04, 0.04)
+    emissionColor: Sequence[float] = (0.0, 0.0, 0.0)
+    emissionIntensity: float = 0.0
+    id: int = 0
+
+    def getEmission(self):
+        return _vec3(self.emissionColor) * np.float32(self.emissionIntensity)
+
+
+@dataclass
+class Light:
+    """Scene.h:17-26."""
+    position: Sequence[float] = (0.0, 0.0, 0.0)
+    color: Sequence[float] = (0.0, 0.0, 0.0)
+    intensity: float = 0.0
+
+
+@dataclass
+class Settings:
+    """Scene.h:49-56."""
+    accumulation: bool = True
+    skyLight: bool = False
+    maxBounces: int = 15
+
+
+class SceneNode:
+    """SceneNode.h:23-66 / SceneNode.cpp."""
+
+    def __init__(self, name: str = "Untitled"):
+        self.m_name = name
+        self.m_position = np.zeros(3, np.float32)
+        self.m_rotation = np.zeros(4, np.float32)  # (x, y, z, w); glm::quat() value-initialises to zeros
+        self.m_scale = np.ones(3, np.float32)
+        self.m_localTransform = IDENTITY.copy()
+        self.m_globalTransform = IDENTITY.copy()
+        self.m_children: List["SceneNode"] = []
+        self.m_spheres: List[Sphere] = []
+        self.m_transformDirty = True
+
+    def setPosition(self, p): self.m_position = _vec3(p); self.m_transformDirty = True
+    def setRotation(self, q_xyzw): self.m_rotation = np.asarray(q_xyzw, np.float32).reshape(4).copy(); self.m_transformDirty = True
+    def setScale(self, s): self.m_scale = _vec3(s); self.m_transformDirty = True
+    def getPosition(self): return self.m_position
+    def getRotation(self): return self.m_rotation
+    def getScale(self): return self.m_scale
+    def addChild(self, child: "SceneNode"): self.m_children.append(child)
+
+    def removeChild(self, child: "SceneNode"):
+        self.m_children = [c for c in self.m_children if c is not child]
+
+    def getChildren(self): return self.m_children
+    def addSphere(self, sphere: Sphere): self.m_spheres.append(sphere)
+
+    def removeSphere(self, index: int):
+        if 0 <= index < len(self.m_spheres):
+            del self.m_spheres[index]
+
+    def getSpheres(self): return self.m_spheres
+    def getName(self): return self.m_name
+    def setName(self, name): self.m_name = name
+    def getGlobalTransform(self): return self.m_globalTransform
+
+    def updateGlobalTransform(self, parentTransform=None):
+        """SceneNode.cpp:42-59."""
+        parent = IDENTITY if parentTransform is None else f32(parentTransform, 16)
+        local = np.empty(16, np.float32)
+        glob = np.empty(16, np.float32)
+        if self.m_transformDirty:
+            check(_capi.lib().atx_host_node_transform(fptr(parent), fptr(self.m_position), fptr(self.m_rotation),
+                                                      fptr(self.m_scale), fptr(local), fptr(glob)))
+            self.m_localTransform = local
+            self.m_transformDirty = False
+        else:
+            glob = _mat_mul(parent, self.m_localTransform)
+        self.m_globalTransform = glob
+        for child in self.m_children:
+            child.updateGlobalTransform(self.m_globalTransform)
+
+
+def _mat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """a * b in glm's mul4x4 order, through the native helper."""
+    out = np.empty(16, np.float32)
+    check(_capi.lib().atx_host_mat4_mul(fptr(f32(a, 16)), fptr(f32(b, 16)), fptr(out)))
+    return out
+
+
+class Camera:
+    """Camera.h:14-88 / Camera.cpp. Input handling (onUpdate) is out of scope (needs a window)."""
+
+    def __init__(self, fov: Optional[float] = None, nearClip: float = 0.1, farClip: float = 100.0,
+                 position=None, direction=None):
+        self.m_projectionMatrix = IDENTITY.copy()
+        self.m_viewMatrix = IDENTITY.copy()
+        self.m_inverseProjectionMatrix = IDENTITY.copy()
+        self.m_inverseViewMatrix = IDENTITY.copy()
+        self.m_position = np.zeros(3, np.float32)
+        self.m_direction = np.zeros(3, np.float32)
+        self.m_rayDirection: Optional[np.ndarray] = None
+        self.m_fov, self.m_nearClip, self.m_farClip = 45.0, 0.1, 100.0
+        self.m_width = self.m_height = 0
+        self.m_viewDirty = self.m_projectionDirty = True
+        if fov is not None:
+            # Camera.cpp:14-29: both value constructors preset 1600x900 and build both matrices
+            self.m_fov, self.m_nearClip, self.m_farClip = float(fov), float(nearClip), float(farClip)
+            self.m_width, self.m_height = 1600, 900
+            if position is None:
+                self.m_direction = _vec3((0.0, 0.0, -1.0))
+                self.m_position = _vec3((0.0, 0.0, 3.0))
+            else:
+                self.m_position = _vec3(position)
+                self.m_direction = _vec3(direction)
+            self._updateViewMatrix()
+            self._updateProjectionMatrix()
+
+    # setters only mark dirty (Camera.h:56-58)
+    def setPosition(self, p): self.m_position = _vec3(p); self.m_viewDirty = True
+    def setDirection(self, d): self.m_direction = _vec3(d); self.m_viewDirty = True
+    def setFov(self, fov): self.m_fov = float(fov); self.m_projectionDirty = True
+    def getPosition(self): return self.m_position
+    def getDirection(self): return self.m_direction
+    def getFov(self): return self.m_fov
+    def getViewMatrix(self): return self.m_viewMatrix
+    def getProjectionMatrix(self): return self.m_projectionMatrix
+    def getInverseViewMatrix(self): return self.m_inverseViewMatrix
+    def getInverseProjectionMatrix(self): return self.m_inverseProjectionMatrix
+    @staticmethod
+    def getRotationSpeed(): return 0.3
+
+    def Resize(self, width: int, height: int):
+        """Camera.cpp:110-127 (including the early return that leaves a 1600x900 camera without rays)."""
+        if width == 0 or height == 0:
+            print("Error: Width or height cannot be zero.")
+            return
+        if width == self.m_width and height == self.m_height:
+            return
+        self.m_width, self.m_height = int(width), int(height)
+        self.m_projectionDirty = True
+        self._updateProjectionMatrix()
+        self.m_rayDirection = None  # rebuilt lazily; the renderer generates rays in-kernel
+
+    def getRayDirection(self) -> np.ndarray:
+        """Camera.h:60 — the host ray table (Camera.cpp:161-195), computed on demand."""
+        if self.m_rayDirection is None:
+            out = np.empty((self.m_height, self.m_width, 3), np.float32)
+            check(_capi.lib().atx_host_ray_directions(fptr(self.m_inverseProjectionMatrix), fptr(self.m_inverseViewMatrix),
+                                                      self.m_width, self.m_height, vptr(out)))
+            self.m_rayDirection = out
+        return self.m_rayDirection
+
+    def _matrices(self):
+        proj, view, iproj, iview = (np.empty(16, np.float32) for _ in range(4))
+        w, h = max(self.m_width, 1), max(self.m_height, 1)
+        check(_capi.lib().atx_host_camera_matrices(fptr(self.m_position), fptr(self.m_direction), self.m_fov,
+                                                   self.m_nearClip, self.m_farClip, w, h,
+                                                   fptr(proj), fptr(view), fptr(iproj), fptr(iview)))
+        return proj, view, iproj, iview
+
+    def _updateProjectionMatrix(self):
+        if self.m_projectionDirty:
+            proj, _, iproj, _ = self._matrices()
+            self.m_projectionMatrix, self.m_inverseProjectionMatrix = proj, iproj
+            self.m_projectionDirty = False
+
+    def _updateViewMatrix(self):
+        if self.m_viewDirty:
+            _, view, _, iview = self._matrices()
+            self.m_viewMatrix, self.m_inverseViewMatrix = view, iview
+            self.m_viewDirty = False
+
+
+@dataclass
+class Scene:
+    """Scene.h:58-80."""
+    rootNode: SceneNode = field(default_factory=lambda: SceneNode("Scene"))
+    materials: List[Material] = field(default_factory=list)
+    lights: List[Light] = field(default_factory=list)
+    settings: Settings = field(default_factory=Settings)
+    camera: Camera = field(default_factory=Camera)
+
+
+class Image:
+    """Headless stand-in for Core/include/Image.h: what Renderer touches (ctor, setData, getWidth/getHeight)."""
+
+    def __init__(self, width: int, height: int):
+        self.m_width, self.m_height = width, height
+        self.data = np.zeros((height, width), np.uint32)
+
+    def getWidth(self): return self.m_width
+    def getHeight(self): return self.m_height
+    def setData(self, data): self.data = data
+
+
+def traverseSceneGraph(node: Optional[SceneNode], parentTransform=None) -> List[Sphere]:
+    """Renderer::traverseSceneGraph (Renderer.cu:67-96): pre-order, world-space centres, mean-scale radii."""
+    out: List[Sphere] = []
+
+    def rec(n: Optional[SceneNode], parent):
+        if n is None:
+            return
+        n.updateGlobalTransform(parent)
+        g = n.getGlobalTransform()
+        for s in n.getSpheres():
+            src = np.zeros(1, SPHERE_DTYPE)
+            src["center"][0] = _vec3(s.center)
+            src["radius"][0] = s.radius
+            src["material"][0] = s.id
+            dst = np.zeros(1, SPHERE_DTYPE)
+            check(_capi.lib().atx_host_transform_sphere(fptr(g), vptr(src), vptr(dst)))
+            out.append(Sphere(tuple(float(v) for v in dst["center"][0]), float(dst["radius"][0]), int(dst["material"][0])))
+        for c in n.getChildren():
+            rec(c, g)
+
+    rec(node, IDENTITY if parentTransform is None else parentTransform)
+    return out
+
+
+def pack_spheres(spheres: Sequence[Sphere]) -> np.ndarray:
+    a = np.zeros(len(spheres), SPHERE_DTYPE)
+    for i, s in enumerate(spheres):
+        a["center"][i] = _vec3(s.center); a["radius"][i] = s.radius; a["material"][i] = s.id
+    return a
+
+
+def pack_materials(materials: Sequence[Material]) -> np.ndarray:
+    a = np.zeros(len(materials), MATERIAL_DTYPE)
+    for i, m in enumerate(materials):
+        a["albedo"][i] = _vec3(m.albedo); a["roughness"][i] = m.roughness; a["metallic"][i] = m.metallic
+        a["F0"][i] = _vec3(m.F0); a["emissionColor"][i] = _vec3(m.emissionColor)
+        a["emissionIntensity"][i] = m.emissionIntensity; a["id"][i] = m.id
+    return a
+
+
+def pack_lights(lights: Sequence[Light]) -> np.ndarray:
+    a = np.zeros(len(lights), LIGHT_DTYPE)
+    for i, l in enumerate(lights):
+        a["position"][i] = _vec3(l.position); a["color"][i] = _vec3(l.color); a["intensity"][i] = l.intensity
+    return a
+
+
+class Renderer:
+    """Renderer.h:19-31 over the C-ABI, plus the headless additions (accumulation read-back,
+    multi-frame launches, counters, spp-split reduce)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(_capi.lib().atx_create(device, C.byref(self._h)))
+        self.m_settings = Settings()
+        self.m_scene = None
+        self.m_image: Optional[Image] = None
+        self.m_width = self.m_height = 0
+        self.variant = _capi.VARIANT_AUTO
+        check(_capi.lib().atx_set_settings(self._h, 1, 0, self.m_settings.maxBounces))
+
+    def close(self):
+        if self._h:
+            _capi.lib().atx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference API ----------------------------------------------------
+    def onResize(self, width: int, height: int):
+        if self.m_image is not None and self.m_image.getWidth() == width and self.m_image.getHeight() == height:
+            return
+        check(_capi.lib().atx_resize(self._h, width, height))
+        self.m_image = Image(width, height)
+        self.m_width, self.m_height = width, height
+
+    def getImage(self): return self.m_image
+    def getSettings(self): return self.m_settings
+
+    def setSettings(self, settings: Settings):
+        self.m_settings = settings
+        check(_capi.lib().atx_set_settings(self._h, int(settings.accumulation), int(settings.skyLight), int(settings.maxBounces)))
+
+    def resetFrameIndex(self):
+        check(_capi.lib().atx_reset(self._h))
+
+    def frameIndex(self) -> int:
+        v = C.c_uint32()
+        check(_capi.lib().atx_frame_index(self._h, C.byref(v)))
+        return v.value
+
+    def Render(self, camera: Camera, scene: Scene, frames: int = 1, readback: bool = True):
+        """Renderer::Render (Renderer.cu:173-249); `frames` > 1 renders that many frames in one launch."""
+        if self.m_scene is not scene or self.frameIndex() == 1:
+            self.m_scene = scene
+            self.uploadScene(scene)  # allocateDeviceMemory, Renderer.cu:175-179
+        if self.m_image is None:
+            return
+        self.setCamera(camera)
+        check(_capi.lib().atx_set_settings(self._h, int(self.m_settings.accumulation), int(self.m_settings.skyLight),
+                                           int(self.m_settings.maxBounces)))
+        check(_capi.lib().atx_render(self._h, frames, self.variant))
+        if readback:
+            check(_capi.lib().atx_read_rgba8(self._h, vptr(self.m_image.data), 0))
+
+    # ---- headless additions -------------------------------------------------
+    def uploadScene(self, scene: Scene):
+        self.uploadArrays(pack_spheres(traverseSceneGraph(scene.rootNode)), pack_materials(scene.materials),
+                          pack_lights(scene.lights))
+
+    def uploadArrays(self, spheres: np.ndarray, materials: np.ndarray, lights: np.ndarray):
+        assert spheres.dtype == SPHERE_DTYPE and materials.dtype == MATERIAL_DTYPE and lights.dtype == LIGHT_DTYPE
+        self._keep = (np.ascontiguousarray(spheres), np.ascontiguousarray(materials), np.ascontiguousarray(lights))
+        s, m, l = self._keep
+        check(_capi.lib().atx_upload_scene(self._h, vptr(s), len(s), vptr(m), len(m), vptr(l), len(l)))
+
+    def setCamera(self, camera: Camera):
+        check(_capi.lib().atx_set_camera_matrices(self._h, fptr(camera.m_position), fptr(camera.m_inverseProjectionMatrix),
+                                                  fptr(camera.m_inverseViewMatrix)))
+
+    def renderFrames(self, first: int, count: int, stride: int = 1, zero_first: bool = False):
+        check(_capi.lib().atx_render_frames(self._h, first, count, stride, int(zero_first), self.variant))
+
+    def sync(self): check(_capi.lib().atx_sync(self._h))
+
+    def lastRenderMs(self) -> float:
+        v = C.c_float()
+        check(_capi.lib().atx_last_render_ms(self._h, C.byref(v)))
+        return v.value
+
+    def setTuning(self, key: int, value: int):
+        check(_capi.lib().atx_set_tuning(self._h, key, value))
+
+    def getAccumulation(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.m_height, self.m_width, 4), np.float32)
+        check(_capi.lib().atx_read_accum(self._h, vptr(out)))
+        return out
+
+    def setAccumulation(self, acc: np.ndarray, next_frame_index: int):
+        a = np.ascontiguousarray(acc, np.float32)
+        check(_capi.lib().atx_write_accum(self._h, vptr(a), next_frame_index))
+
+    def getRGBA8(self, divisor: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.m_height, self.m_width), np.uint32)
+        check(_capi.lib().atx_read_rgba8(self._h, vptr(out), divisor))
+        return out
+
+    def getHitIds(self) -> np.ndarray:
+        out = np.empty((self.m_height, self.m_width), np.int32)
+        check(_capi.lib().atx_read_hit_ids(self._h, vptr(out)))
+        return out
+
+    def getRayDirections(self) -> np.ndarray:
+        out = np.empty((self.m_height, self.m_width, 3), np.float32)
+        check(_capi.lib().atx_read_ray_directions(self._h, vptr(out)))
+        return out
+
+    def counters(self) -> _capi.Counters:
+        c = _capi.Counters()
+        check(_capi.lib().atx_get_counters(self._h, C.byref(c)))
+        return c
+
+    def resetCounters(self): check(_capi.lib().atx_reset_counters(self._h))
+
+    def accumDevicePtr(self) -> int:
+        p = C.c_void_p()
+        check(_capi.lib().atx_accum_device_ptr(self._h, C.byref(p)))
+        return p.value or 0
+
+    # multi-GPU
+    @staticmethod
+    def commUniqueId() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(_capi.lib().atx_comm_unique_id(buf))
+        return bytes(buf)
+
+    def commInitRank(self, n_ranks: int, rank: int, uid: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        check(_capi.lib().atx_comm_init_rank(self._h, n_ranks, rank, buf))
+
+    def commDestroy(self): check(_capi.lib().atx_comm_destroy(self._h))
+    def allreduceAccum(self): check(_capi.lib().atx_allreduce_accum(self._h))

@@ -1,0 +1,801 @@
+// atx_capi.cu — the C-ABI (include/ataraxia_b200.h) over the sm_100a kernels.
+//
+// This is the headless host layer that replaces the reference's
+// Renderer::Render choreography (Renderer.cu:173-249): no per-frame cudaMalloc,
+// no per-frame W*H*12 B ray-table upload (Camera.cpp:197-210), no device-wide
+// syncs; one non-default stream per handle; status codes instead of exit().
+// There is no CPU fallback anywhere in this file: every render entry point
+// launches CUDA kernels or fails.
+#include "../../include/ataraxia_b200.h"
+#include "../../include/ataraxia/Math.h"
+#include "atx_device.cuh"
+#include "atx_kernels.h"
+
+#include <dlfcn.h>
+#include <nccl.h> // types and enums only; the library is resolved at run time with dlopen
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace
+{
+thread_local std::string g_lastError;
+
+atx_status fail(atx_status code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define ATX_CUDA(call)                                                                                         \
+    do                                                                                                         \
+    {                                                                                                          \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return fail(ATX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL, resolved lazily so the library loads on hosts without it ----------
+struct NcclApi
+{
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried)
+        return api;
+    tried = true;
+    // a process that already carries NCCL (e.g. torch's bundled copy) gets that same
+    // instance back from dlopen by soname; otherwise the system library is loaded
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names)
+    {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib)
+            break;
+    }
+    if (!api.lib)
+        return api;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    return api;
+}
+
+struct CameraState
+{
+    bool set = false;
+    bool fromParams = false;
+    float pos[3] = { 0, 0, 0 }, dir[3] = { 0, 0, -1 };
+    float fov = 45.0f, nearClip = 0.1f, farClip = 100.0f;
+    atx::mat4 invProj{ 1.0f }, invView{ 1.0f };
+};
+
+void camera_matrices(const float pos[3], const float dir[3], float fov, float nearClip, float farClip, uint32_t w,
+                     uint32_t h, atx::mat4& proj, atx::mat4& view, atx::mat4& invProj, atx::mat4& invView)
+{
+    // Camera::UpdateProjectionMatrix (Camera.cpp:134-149) and UpdateViewMatrix (:151-159)
+    const float aspect = static_cast<float>(w) / static_cast<float>(h);
+    proj = atx::perspective(atx::radians(fov), aspect, nearClip, farClip);
+    invProj = atx::inverse(proj);
+    const atx::vec3 p(pos[0], pos[1], pos[2]), d(dir[0], dir[1], dir[2]);
+    view = atx::lookAt(p, p + d, atx::vec3(0.0f, 1.0f, 0.0f));
+    invView = atx::inverse(view);
+}
+} // namespace
+
+struct atx_renderer
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool timed = false;
+
+    uint32_t width = 0, height = 0;
+    float4* dAccum = nullptr;
+    uint32_t* dRgba = nullptr;
+    int32_t* dHit = nullptr;   // lazily allocated debug buffers
+    float* dRays = nullptr;
+    unsigned long long* dCounters = nullptr;
+
+    // scene
+    float *dSphAoS = nullptr, *dMatAoS = nullptr, *dLightAoS = nullptr;
+    float4 *dSpheres = nullptr, *dMats = nullptr, *dLights = nullptr;
+    int32_t* dSphMat = nullptr;
+    size_t capS = 0, capM = 0, capL = 0;
+    uint32_t nS = 0, nM = 0, nL = 0;
+
+    CameraState cam;
+    bool accumulation = true, skyLight = false;
+    int maxBounces = 15; // Settings default, Scene.h:53
+    uint32_t frameIndex = 1;
+    uint32_t lastFrame = 1;     // frameIndex of the last rendered frame (display divisor)
+    uint32_t chunkOverride = 0; // tuning: force the shared-memory chunk size (spheres)
+    uint64_t launches = 0;
+
+    ncclComm_t comm = nullptr;
+    int nRanks = 1, rank = 0;
+};
+
+namespace
+{
+atx_status make_params(atx_handle h, atxk::RenderParams& p)
+{
+    if (h->width == 0 || h->height == 0)
+        return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    if (!h->cam.set)
+        return fail(ATX_ERR_INVALID, "no camera: call atx_set_camera or atx_set_camera_matrices");
+    std::memset(&p, 0, sizeof(p));
+    p.width = h->width;
+    p.height = h->height;
+    p.maxBounces = h->maxBounces;
+    p.skyLight = h->skyLight ? 1 : 0;
+    p.nSpheres = h->nS;
+    p.nMaterials = h->nM;
+    p.nLights = h->nL;
+    p.spheres = h->dSpheres;
+    p.sphMat = h->dSphMat;
+    p.mats = h->dMats;
+    p.lights = h->dLights;
+    p.accum = h->dAccum;
+    p.rgba = h->dRgba;
+    p.counters = h->dCounters;
+    // shared-memory plan: whole scene if it fits the two-CTAs-per-SM budget, else chunks
+    uint32_t chunk = h->nS;
+    const uint32_t fit = atx_launch::kSmemBudgetTwoCtas / sizeof(float4);
+    if (h->chunkOverride)
+        chunk = h->chunkOverride;
+    else if (h->nS > fit)
+        chunk = fit / 2; // double-buffered
+    p.chunkSpheres = chunk ? chunk : 1;
+    const atx::mat4& ip = h->cam.invProj;
+    const atx::mat4& iv = h->cam.invView;
+    for (int i = 0; i < 4; i++)
+    {
+        p.cam.ip0[i] = ip[0][i];
+        p.cam.ip1[i] = ip[1][i];
+        // (m2*1 + m3*1): the constant half of glm's mat4*vec4 (type_mat4x4.inl:568-571)
+        p.cam.ipA1[i] = ip[2][i] * 1.0f + ip[3][i] * 1.0f;
+    }
+    for (int i = 0; i < 3; i++)
+    {
+        p.cam.iv0[i] = iv[0][i];
+        p.cam.iv1[i] = iv[1][i];
+        p.cam.iv2[i] = iv[2][i];
+        p.cam.iv3z[i] = iv[3][i] * 0.0f;
+        p.cam.pos[i] = h->cam.pos[i];
+    }
+    return ATX_OK;
+}
+
+atx_status ensure_device(atx_handle h)
+{
+    if (!h)
+        return fail(ATX_ERR_INVALID, "null handle");
+    ATX_CUDA(cudaSetDevice(h->device));
+    return ATX_OK;
+}
+
+template <typename T>
+atx_status grow(T*& ptr, size_t& cap, size_t need, size_t elemsPer)
+{
+    if (need <= cap && ptr)
+        return ATX_OK;
+    if (ptr)
+        ATX_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    const size_t n = std::max<size_t>(need, 1);
+    ATX_CUDA(cudaMalloc(&ptr, n * elemsPer * sizeof(T)));
+    cap = n;
+    return ATX_OK;
+}
+} // namespace
+
+extern "C" {
+
+const char* atx_last_error(void) { return g_lastError.c_str(); }
+
+const char* atx_version(void) { return "ataraxia_b200 0.1 (sm_100a; C-ABI 1)"; }
+
+atx_status atx_create(int device_ordinal, atx_handle* out)
+{
+    if (!out)
+        return fail(ATX_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ATX_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return fail(ATX_ERR_INVALID, "device ordinal %d out of range [0,%d)", device_ordinal, count);
+    ATX_CUDA(cudaSetDevice(device_ordinal));
+    atx_renderer* h = new (std::nothrow) atx_renderer();
+    if (!h)
+        return fail(ATX_ERR_ALLOC, "out of host memory");
+    h->device = device_ordinal;
+    ATX_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    ATX_CUDA(cudaEventCreate(&h->evStart));
+    ATX_CUDA(cudaEventCreate(&h->evStop));
+    ATX_CUDA(cudaMalloc(&h->dCounters, 4 * sizeof(unsigned long long)));
+    ATX_CUDA(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned long long), h->stream));
+    ATX_CUDA(atx_launch::configure());
+    *out = h;
+    return ATX_OK;
+}
+
+atx_status atx_destroy(atx_handle h)
+{
+    if (!h)
+        return ATX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl().ok)
+        nccl().CommDestroy(h->comm);
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters);
+    cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
+    cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
+    cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return ATX_OK;
+}
+
+atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (width == 0 || height == 0)
+        return fail(ATX_ERR_INVALID, "width or height cannot be zero");
+    if (h->dAccum && h->width == width && h->height == height)
+        return ATX_OK; // Renderer.cu:100-101
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays);
+    h->dAccum = nullptr; h->dRgba = nullptr; h->dHit = nullptr; h->dRays = nullptr;
+    const size_t P = static_cast<size_t>(width) * height;
+    ATX_CUDA(cudaMalloc(&h->dAccum, P * sizeof(float4)));
+    ATX_CUDA(cudaMalloc(&h->dRgba, P * sizeof(uint32_t)));
+    ATX_CUDA(cudaMemsetAsync(h->dAccum, 0, P * sizeof(float4), h->stream));
+    ATX_CUDA(cudaMemsetAsync(h->dRgba, 0, P * sizeof(uint32_t), h->stream));
+    h->width = width;
+    h->height = height;
+    h->frameIndex = 1; // Renderer.cu:145
+    h->lastFrame = 1;
+    if (h->cam.set && h->cam.fromParams)
+    {
+        atx::mat4 proj, view;
+        camera_matrices(h->cam.pos, h->cam.dir, h->cam.fov, h->cam.nearClip, h->cam.farClip, width, height, proj, view,
+                        h->cam.invProj, h->cam.invView);
+    }
+    return ATX_OK;
+}
+
+atx_status atx_upload_scene(atx_handle h, const atx_sphere* spheres, size_t n_spheres, const atx_material* materials,
+                            size_t n_materials, const atx_light* lights, size_t n_lights)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if ((n_spheres && !spheres) || (n_materials && !materials) || (n_lights && !lights))
+        return fail(ATX_ERR_INVALID, "null array with non-zero count");
+    if (n_spheres > 0x7fffffffu || n_materials > 0x7fffffffu || n_lights > 0x7fffffffu)
+        return fail(ATX_ERR_INVALID, "scene too large");
+    static_assert(sizeof(atx_sphere) == 20 && sizeof(atx_material) == 52 && sizeof(atx_light) == 28, "POD layout");
+    size_t c;
+    c = h->capS; if (atx_status s = grow(h->dSphAoS, c, n_spheres, 5)) return s;
+    c = h->capS; if (atx_status s = grow(h->dSphMat, c, n_spheres, 1)) return s;
+    if (atx_status s = grow(h->dSpheres, h->capS, n_spheres, 1)) return s;
+    c = h->capM; if (atx_status s = grow(h->dMatAoS, c, n_materials, 13)) return s;
+    if (atx_status s = grow(h->dMats, h->capM, n_materials, atxk::kMatStride)) return s;
+    c = h->capL; if (atx_status s = grow(h->dLightAoS, c, n_lights, 7)) return s;
+    if (atx_status s = grow(h->dLights, h->capL, n_lights, atxk::kLightStride)) return s;
+    if (n_spheres)
+        ATX_CUDA(cudaMemcpyAsync(h->dSphAoS, spheres, n_spheres * sizeof(atx_sphere), cudaMemcpyHostToDevice, h->stream));
+    if (n_materials)
+        ATX_CUDA(cudaMemcpyAsync(h->dMatAoS, materials, n_materials * sizeof(atx_material), cudaMemcpyHostToDevice, h->stream));
+    if (n_lights)
+        ATX_CUDA(cudaMemcpyAsync(h->dLightAoS, lights, n_lights * sizeof(atx_light), cudaMemcpyHostToDevice, h->stream));
+    h->nS = static_cast<uint32_t>(n_spheres);
+    h->nM = static_cast<uint32_t>(n_materials);
+    h->nL = static_cast<uint32_t>(n_lights);
+    ATX_CUDA(atx_launch::pack_scene(h->dSphAoS, h->nS, h->dMatAoS, h->nM, h->dLightAoS, h->nL, h->dSpheres, h->dSphMat,
+                                    h->dMats, h->dLights, h->stream));
+    h->launches++;
+    // the caller's arrays may be pageable: the copies above must have consumed them before we return
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_set_camera(atx_handle h, const float position[3], const float direction[3], float fov_degrees,
+                          float near_clip, float far_clip)
+{
+    if (!h || !position || !direction)
+        return fail(ATX_ERR_INVALID, "null argument");
+    if (h->width == 0 || h->height == 0)
+        return fail(ATX_ERR_INVALID, "atx_resize must precede atx_set_camera (the projection needs the aspect ratio)");
+    std::memcpy(h->cam.pos, position, 12);
+    std::memcpy(h->cam.dir, direction, 12);
+    h->cam.fov = fov_degrees;
+    h->cam.nearClip = near_clip;
+    h->cam.farClip = far_clip;
+    atx::mat4 proj, view;
+    camera_matrices(h->cam.pos, h->cam.dir, fov_degrees, near_clip, far_clip, h->width, h->height, proj, view,
+                    h->cam.invProj, h->cam.invView);
+    h->cam.set = true;
+    h->cam.fromParams = true;
+    return ATX_OK;
+}
+
+atx_status atx_set_camera_matrices(atx_handle h, const float position[3], const float inv_projection[16],
+                                   const float inv_view[16])
+{
+    if (!h || !position || !inv_projection || !inv_view)
+        return fail(ATX_ERR_INVALID, "null argument");
+    std::memcpy(h->cam.pos, position, 12);
+    std::memcpy(&h->cam.invProj, inv_projection, 64);
+    std::memcpy(&h->cam.invView, inv_view, 64);
+    h->cam.set = true;
+    h->cam.fromParams = false;
+    return ATX_OK;
+}
+
+atx_status atx_set_settings(atx_handle h, int accumulation, int sky_light, int max_bounces)
+{
+    if (!h)
+        return fail(ATX_ERR_INVALID, "null handle");
+    h->accumulation = accumulation != 0;
+    h->skyLight = sky_light != 0;
+    h->maxBounces = max_bounces;
+    return ATX_OK;
+}
+
+atx_status atx_set_tuning(atx_handle h, int key, int64_t value)
+{
+    if (!h)
+        return fail(ATX_ERR_INVALID, "null handle");
+    switch (key)
+    {
+    case ATX_TUNE_CHUNK_SPHERES:
+        if (value < 0 || value > 7000)
+            return fail(ATX_ERR_INVALID, "chunk_spheres must be in [0, 7000] (0 = automatic)");
+        h->chunkOverride = static_cast<uint32_t>(value);
+        return ATX_OK;
+    default:
+        return fail(ATX_ERR_INVALID, "unknown tuning key %d", key);
+    }
+}
+
+atx_status atx_reset(atx_handle h)
+{
+    if (!h)
+        return fail(ATX_ERR_INVALID, "null handle");
+    h->frameIndex = 1;
+    return ATX_OK;
+}
+
+atx_status atx_frame_index(atx_handle h, uint32_t* out)
+{
+    if (!h || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    *out = h->frameIndex;
+    return ATX_OK;
+}
+
+static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32_t stride, bool zeroFirst, int variant,
+                                bool emitRgba, uint32_t rgbaDivisor)
+{
+    if (variant != ATX_VARIANT_AUTO && variant != ATX_VARIANT_MEGAKERNEL && variant != ATX_VARIANT_WAVEFRONT)
+        return fail(ATX_ERR_INVALID, "unknown variant %d", variant);
+    if (variant == ATX_VARIANT_WAVEFRONT)
+        return fail(ATX_ERR_INVALID, "the wavefront variant is not built in this version");
+    atxk::RenderParams p;
+    if (atx_status s = make_params(h, p))
+        return s;
+    p.firstFrame = first;
+    p.nFrames = n;
+    p.frameStride = stride;
+    p.zeroFirst = zeroFirst ? 1 : 0;
+    p.emitRgba = emitRgba ? 1 : 0;
+    p.rgbaDivisor = rgbaDivisor;
+    if (atx_launch::megakernel_smem_bytes(p) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
+        return fail(ATX_ERR_INVALID, "shared-memory plan exceeds the device limit");
+    ATX_CUDA(atx_launch::render_mega(p, h->stream));
+    h->launches++;
+    return ATX_OK;
+}
+
+atx_status atx_render(atx_handle h, uint32_t n_frames, int variant)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (n_frames == 0)
+        return ATX_OK;
+    ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
+    if (h->accumulation)
+    {
+        const uint32_t first = h->frameIndex;
+        const uint32_t last = first + n_frames - 1;
+        if (atx_status s = launch_frames(h, first, n_frames, 1, first == 1, variant, true, last))
+            return s;
+        h->lastFrame = last;
+        h->frameIndex = last + 1; // Renderer.cu:245-246
+    }
+    else
+    {
+        // accumulation off: every frame restarts from a cleared buffer at frameIndex 1 (Renderer.cu:181-182, :247-248)
+        for (uint32_t k = 0; k < n_frames; k++)
+            if (atx_status s = launch_frames(h, 1, 1, 1, true, variant, true, 1))
+                return s;
+        h->lastFrame = 1;
+        h->frameIndex = 1;
+    }
+    ATX_CUDA(cudaEventRecord(h->evStop, h->stream));
+    h->timed = true;
+    return ATX_OK;
+}
+
+atx_status atx_render_frames(atx_handle h, uint32_t first_frame, uint32_t n_frames, uint32_t frame_stride,
+                             int zero_first, int variant)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (frame_stride == 0)
+        return fail(ATX_ERR_INVALID, "frame_stride must be >= 1");
+    ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
+    if (n_frames == 0)
+    {
+        if (zero_first)
+            ATX_CUDA(cudaMemsetAsync(h->dAccum, 0, static_cast<size_t>(h->width) * h->height * sizeof(float4), h->stream));
+    }
+    else
+    {
+        if (atx_status s = launch_frames(h, first_frame, n_frames, frame_stride, zero_first != 0, variant, false, 1))
+            return s;
+        h->lastFrame = first_frame + (n_frames - 1) * frame_stride;
+    }
+    ATX_CUDA(cudaEventRecord(h->evStop, h->stream));
+    h->timed = true;
+    return ATX_OK;
+}
+
+atx_status atx_sync(atx_handle h)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_last_render_ms(atx_handle h, float* out_ms)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!out_ms)
+        return fail(ATX_ERR_INVALID, "out_ms is null");
+    if (!h->timed)
+        return fail(ATX_ERR_INVALID, "nothing rendered yet");
+    ATX_CUDA(cudaEventSynchronize(h->evStop));
+    ATX_CUDA(cudaEventElapsedTime(out_ms, h->evStart, h->evStop));
+    return ATX_OK;
+}
+
+atx_status atx_read_accum(atx_handle h, float* dst)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!dst || !h->dAccum)
+        return fail(ATX_ERR_INVALID, "no destination or no image");
+    const size_t bytes = static_cast<size_t>(h->width) * h->height * sizeof(float4);
+    ATX_CUDA(cudaMemcpyAsync(dst, h->dAccum, bytes, cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_write_accum(atx_handle h, const float* src, uint32_t next_frame_index)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!src || !h->dAccum || next_frame_index == 0)
+        return fail(ATX_ERR_INVALID, "no source, no image, or frame index 0");
+    const size_t bytes = static_cast<size_t>(h->width) * h->height * sizeof(float4);
+    ATX_CUDA(cudaMemcpyAsync(h->dAccum, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    h->frameIndex = next_frame_index;
+    h->lastFrame = next_frame_index > 1 ? next_frame_index - 1 : 1;
+    return ATX_OK;
+}
+
+atx_status atx_read_rgba8(atx_handle h, uint32_t* dst, uint32_t divisor)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!dst || !h->dRgba)
+        return fail(ATX_ERR_INVALID, "no destination or no image");
+    const uint32_t n = h->width * h->height;
+    if (divisor != 0)
+    {
+        // explicit divisor (e.g. total spp after a multi-GPU reduce): re-resolve on the device
+        ATX_CUDA(atx_launch::resolve_rgba(h->dAccum, h->dRgba, n, divisor, h->stream));
+        h->launches++;
+    }
+    ATX_CUDA(cudaMemcpyAsync(dst, h->dRgba, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_read_hit_ids(atx_handle h, int32_t* dst)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!dst)
+        return fail(ATX_ERR_INVALID, "dst is null");
+    atxk::RenderParams p;
+    if (atx_status s = make_params(h, p))
+        return s;
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    if (!h->dHit)
+        ATX_CUDA(cudaMalloc(&h->dHit, P * sizeof(int32_t)));
+    ATX_CUDA(atx_launch::primary_hits(p, h->dHit, h->stream));
+    h->launches++;
+    ATX_CUDA(cudaMemcpyAsync(dst, h->dHit, P * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_read_ray_directions(atx_handle h, float* dst)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!dst)
+        return fail(ATX_ERR_INVALID, "dst is null");
+    atxk::RenderParams p;
+    if (atx_status s = make_params(h, p))
+        return s;
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    if (!h->dRays)
+        ATX_CUDA(cudaMalloc(&h->dRays, P * 3 * sizeof(float)));
+    ATX_CUDA(atx_launch::ray_directions(p, h->dRays, h->stream));
+    h->launches++;
+    ATX_CUDA(cudaMemcpyAsync(dst, h->dRays, P * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_get_counters(atx_handle h, atx_counters* out)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!out)
+        return fail(ATX_ERR_INVALID, "out is null");
+    unsigned long long c[4];
+    ATX_CUDA(cudaMemcpyAsync(c, h->dCounters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    out->paths = c[0];
+    out->rays = c[1];
+    out->sphere_tests = c[1] * h->nS; // every traceRay tests every sphere (Renderer.cu:256)
+    out->launches = h->launches;
+    return ATX_OK;
+}
+
+atx_status atx_reset_counters(atx_handle h)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    ATX_CUDA(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned long long), h->stream));
+    h->launches = 0;
+    return ATX_OK;
+}
+
+atx_status atx_accum_device_ptr(atx_handle h, void** out)
+{
+    if (!h || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    *out = h->dAccum;
+    return ATX_OK;
+}
+
+atx_status atx_stream(atx_handle h, void** out_cuda_stream)
+{
+    if (!h || !out_cuda_stream)
+        return fail(ATX_ERR_INVALID, "null argument");
+    *out_cuda_stream = h->stream;
+    return ATX_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------
+
+atx_status atx_comm_unique_id(uint8_t id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (!id)
+        return fail(ATX_ERR_INVALID, "id is null");
+    if (!nccl().ok)
+        return fail(ATX_ERR_NCCL, "NCCL library not loadable: %s", dlerror() ? dlerror() : "symbols missing");
+    ncclUniqueId uid;
+    ncclResult_t r = nccl().GetUniqueId(&uid);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclGetUniqueId: %s", nccl().GetErrorString(r));
+    std::memcpy(id, &uid, 128);
+    return ATX_OK;
+}
+
+atx_status atx_comm_init_rank(atx_handle h, int n_ranks, int rank, const uint8_t id[128])
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(ATX_ERR_INVALID, "bad communicator arguments");
+    if (!nccl().ok)
+        return fail(ATX_ERR_NCCL, "NCCL library not loadable");
+    if (h->comm)
+    {
+        nccl().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, 128);
+    ncclResult_t r = nccl().CommInitRank(&h->comm, n_ranks, uid, rank);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclCommInitRank: %s", nccl().GetErrorString(r));
+    h->nRanks = n_ranks;
+    h->rank = rank;
+    return ATX_OK;
+}
+
+atx_status atx_comm_destroy(atx_handle h)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (h->comm && nccl().ok)
+    {
+        cudaStreamSynchronize(h->stream);
+        nccl().CommDestroy(h->comm);
+    }
+    h->comm = nullptr;
+    h->nRanks = 1;
+    h->rank = 0;
+    return ATX_OK;
+}
+
+atx_status atx_allreduce_accum(atx_handle h)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!h->comm)
+        return fail(ATX_ERR_INVALID, "no communicator: call atx_comm_init_rank");
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "no image");
+    const size_t count = static_cast<size_t>(h->width) * h->height * 4;
+    ncclResult_t r = nccl().AllReduce(h->dAccum, h->dAccum, count, ncclFloat32, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+    return ATX_OK;
+}
+
+// ---- host math helpers for the header-only C++ mirror -------------------------
+// Compiled here (not in the caller) so the caller's compiler flags cannot change
+// the numerics that parity depends on.
+
+atx_status atx_host_camera_matrices(const float position[3], const float direction[3], float fov_degrees,
+                                    float near_clip, float far_clip, uint32_t width, uint32_t height,
+                                    float projection[16], float view[16], float inv_projection[16], float inv_view[16])
+{
+    if (!position || !direction || width == 0 || height == 0)
+        return fail(ATX_ERR_INVALID, "bad camera arguments");
+    atx::mat4 p, v, ip, iv;
+    camera_matrices(position, direction, fov_degrees, near_clip, far_clip, width, height, p, v, ip, iv);
+    if (projection) std::memcpy(projection, &p, 64);
+    if (view) std::memcpy(view, &v, 64);
+    if (inv_projection) std::memcpy(inv_projection, &ip, 64);
+    if (inv_view) std::memcpy(inv_view, &iv, 64);
+    return ATX_OK;
+}
+
+atx_status atx_host_ray_directions(const float inv_projection[16], const float inv_view[16], uint32_t width,
+                                   uint32_t height, float* out)
+{
+    // Camera::UpdateRayDirection (Camera.cpp:161-195) for callers of Camera::getRayDirection():
+    // the renderer itself never reads this table — it generates rays in-kernel.
+    if (!inv_projection || !inv_view || !out || width == 0 || height == 0)
+        return fail(ATX_ERR_INVALID, "bad arguments");
+    atx::mat4 ip, iv;
+    std::memcpy(&ip, inv_projection, 64);
+    std::memcpy(&iv, inv_view, 64);
+    const int nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), height));
+    std::vector<std::thread> threads;
+    const uint32_t rows = height / nThreads;
+    for (int t = 0; t < nThreads; t++)
+    {
+        const uint32_t y0 = t * rows, y1 = (t == nThreads - 1) ? height : y0 + rows;
+        threads.emplace_back([=]() {
+            for (uint32_t y = y0; y < y1; y++)
+                for (uint32_t x = 0; x < width; x++)
+                {
+                    atx::vec2 coord(static_cast<float>(x) / static_cast<float>(width),
+                                    static_cast<float>(y) / static_cast<float>(height));
+                    coord = coord * 2.0f - 1.0f;
+                    const atx::vec4 target = ip * atx::vec4(coord.x, coord.y, 1.0f, 1.0f);
+                    const atx::vec3 n = atx::normalize(atx::vec3(target.x, target.y, target.z) / target.w);
+                    const atx::vec4 r = iv * atx::vec4(n, 0.0f);
+                    const atx::vec3 d = atx::normalize(atx::vec3(r.x, r.y, r.z));
+                    float* o = out + 3ull * (x + static_cast<size_t>(y) * width);
+                    o[0] = d.x; o[1] = d.y; o[2] = d.z;
+                }
+        });
+    }
+    for (auto& th : threads)
+        th.join();
+    return ATX_OK;
+}
+
+atx_status atx_host_node_transform(const float parent[16], const float position[3], const float rotation_xyzw[4],
+                                   const float scale[3], float local[16], float global[16])
+{
+    // SceneNode::updateGlobalTransform (SceneNode.cpp:42-59)
+    if (!parent || !position || !rotation_xyzw || !scale)
+        return fail(ATX_ERR_INVALID, "null argument");
+    atx::mat4 par;
+    std::memcpy(&par, parent, 64);
+    const atx::quat q(rotation_xyzw[3], rotation_xyzw[0], rotation_xyzw[1], rotation_xyzw[2]);
+    const atx::mat4 loc = atx::translate(atx::mat4(1.0f), atx::vec3(position[0], position[1], position[2])) *
+                          atx::mat4_cast(q) * atx::scale(atx::mat4(1.0f), atx::vec3(scale[0], scale[1], scale[2]));
+    const atx::mat4 glob = par * loc;
+    if (local) std::memcpy(local, &loc, 64);
+    if (global) std::memcpy(global, &glob, 64);
+    return ATX_OK;
+}
+
+atx_status atx_host_mat4_mul(const float a[16], const float b[16], float out[16])
+{
+    if (!a || !b || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    atx::mat4 A, B;
+    std::memcpy(&A, a, 64);
+    std::memcpy(&B, b, 64);
+    const atx::mat4 R = A * B;
+    std::memcpy(out, &R, 64);
+    return ATX_OK;
+}
+
+atx_status atx_host_transform_sphere(const float global[16], const atx_sphere* in, atx_sphere* out)
+{
+    // Renderer::traverseSceneGraph, per sphere (Renderer.cu:77-88)
+    if (!global || !in || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    atx::mat4 g;
+    std::memcpy(&g, global, 64);
+    const atx::vec4 c = g * atx::vec4(in->center[0], in->center[1], in->center[2], 1.0f);
+    const atx::vec3 c3 = atx::vec3(c.x, c.y, c.z) / c.w;
+    const float sx = atx::length(atx::vec3(g[0].x, g[0].y, g[0].z));
+    const float sy = atx::length(atx::vec3(g[1].x, g[1].y, g[1].z));
+    const float sz = atx::length(atx::vec3(g[2].x, g[2].y, g[2].z));
+    const float uniformScale = (sx + sy + sz) / 3.0f;
+    *out = *in;
+    out->center[0] = c3.x; out->center[1] = c3.y; out->center[2] = c3.z;
+    out->radius = in->radius * uniformScale; // "radius *= uniformScale"
+    return ATX_OK;
+}
+
+} // extern "C"

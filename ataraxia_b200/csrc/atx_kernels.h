@@ -1,0 +1,27 @@
+// atx_kernels.h — host-side declarations of the kernel launchers (atx_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace atxk
+{
+struct RenderParams;
+}
+
+namespace atx_launch
+{
+// dynamic shared memory the megakernel may opt in to (227 KB is the sm_100 per-CTA limit;
+// the default budget keeps two CTAs resident per SM)
+constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kSmemBudgetTwoCtas = 100 * 1024;
+
+cudaError_t configure();
+cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, uint32_t nM, const float* lightAoS,
+                       uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);
+size_t megakernel_smem_bytes(const atxk::RenderParams& p);
+cudaError_t render_mega(const atxk::RenderParams& p, cudaStream_t s);
+cudaError_t primary_hits(const atxk::RenderParams& p, int32_t* out, cudaStream_t s);
+cudaError_t ray_directions(const atxk::RenderParams& p, float* out, cudaStream_t s);
+cudaError_t resolve_rgba(const float4* accum, uint32_t* rgba, uint32_t n, uint32_t divisor, cudaStream_t s);
+}

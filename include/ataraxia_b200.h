@@ -1,0 +1,254 @@
+/*
+ * ataraxia_b200.h — C-ABI of the B200-native path-tracing hot path.
+ *
+ * This is the drop-in boundary. The reference (1neskk/Ataraxia)
+ * has no FFI layer: its boundary is the C++ class API in Engine/include. The
+ * C++ mirror of that API (include/ataraxia/*.h: Renderer, Scene, SceneNode,
+ * Camera, Material, Light, Settings, Utils) is a thin host layer over the
+ * functions declared here, and every function cites the reference code it
+ * replaces. Plain pointers and sizes only; no torch / glm / STL types.
+ *
+ * Conventions
+ *   - every function returns an atx_status (0 = ok, negative = error); the
+ *     message of the last error on the calling thread is atx_last_error().
+ *     Nothing here ever calls exit() (the reference's CUDA_CHECK does,
+ *     Engine/include/DeviceMemory.h:7-16).
+ *   - one handle = one device + one non-default CUDA stream; handles are
+ *     independent; a handle is not thread-safe.
+ *   - host arrays passed in are copied during the call; output pointers are
+ *     caller-allocated HOST memory unless the name says "_device".
+ *   - there is NO CPU fallback: without a CUDA device atx_create fails.
+ */
+#ifndef ATARAXIA_B200_H
+#define ATARAXIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ATX_API __declspec(dllexport)
+#else
+#define ATX_API __attribute__((visibility("default")))
+#endif
+
+typedef int atx_status;
+enum {
+    ATX_OK = 0,
+    ATX_ERR_INVALID = -1,   /* bad argument / bad state */
+    ATX_ERR_CUDA = -2,      /* CUDA runtime error (message has the string) */
+    ATX_ERR_NCCL = -3,      /* NCCL error or NCCL library not loadable */
+    ATX_ERR_NO_DEVICE = -4, /* no CUDA device: there is no CPU fallback */
+    ATX_ERR_ALLOC = -5
+};
+
+/* POD scene records. Byte-identical to the reference's structs so a caller can
+ * pass std::vector<Sphere>::data() etc. unchanged. */
+typedef struct atx_sphere {   /* == Sphere, Engine/include/SceneNode.h:11-21 (20 B) */
+    float center[3];
+    float radius;
+    int32_t material;         /* Sphere::id = material index */
+} atx_sphere;
+
+typedef struct atx_material { /* == Material, Engine/include/Scene.h:28-47 (52 B) */
+    float albedo[3];
+    float roughness;
+    float metallic;
+    float F0[3];
+    float emissionColor[3];
+    float emissionIntensity;
+    int32_t id;
+} atx_material;
+
+typedef struct atx_light {    /* == Light, Engine/include/Scene.h:17-26 (28 B) */
+    float position[3];
+    float color[3];
+    float intensity;
+} atx_light;
+
+typedef struct atx_counters {
+    uint64_t paths;           /* perPixel evaluations (pixel x sample) */
+    uint64_t rays;            /* traceRay calls (closest-hit + shadow) */
+    uint64_t sphere_tests;    /* rays x numSpheres (brute force, Renderer.cu:256) */
+    uint64_t launches;        /* kernels of this library launched on the handle */
+} atx_counters;
+
+/* kernel family for atx_render* */
+enum {
+    ATX_VARIANT_AUTO = 0,      /* pick by measured divergence */
+    ATX_VARIANT_MEGAKERNEL = 1,/* one persistent path loop per pixel, path regeneration */
+    ATX_VARIANT_WAVEFRONT = 2  /* per-bounce queues with ray compaction */
+};
+
+typedef struct atx_renderer* atx_handle;
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* Create a renderer on CUDA device `device_ordinal` (reference: Renderer::Renderer,
+ * Renderer.cu:13-15, which implies device 0). Fails with ATX_ERR_NO_DEVICE when
+ * no CUDA device is present. */
+ATX_API atx_status atx_create(int device_ordinal, atx_handle* out);
+
+/* Renderer::~Renderer, Renderer.cu:17-23. */
+ATX_API atx_status atx_destroy(atx_handle h);
+
+/* Message of the last failing call on this thread ("" if none). */
+ATX_API const char* atx_last_error(void);
+
+/* Library/ABI version and the SM architecture the kernels were built for. */
+ATX_API const char* atx_version(void);
+
+/* ---- state --------------------------------------------------------------- */
+
+/* Renderer::onResize, Renderer.cu:98-146: (re)allocates the RGBA8 image and the
+ * float4 accumulation buffer and resets frameIndex to 1. No-op when the size is
+ * unchanged. Zero width/height is ATX_ERR_INVALID (reference prints and returns,
+ * Camera.cpp:112-116). */
+ATX_API atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height);
+
+/* Renderer::allocateDeviceMemory, Renderer.cu:25-57, for an already flattened
+ * scene (world-space spheres from Renderer::traverseSceneGraph, :67-96).
+ * Sphere material indices >= n_materials (as unsigned) are clamped to 0 exactly
+ * as Renderer.cu:30-37 does. The library packs SoA records for shared memory. */
+ATX_API atx_status atx_upload_scene(atx_handle h,
+                                    const atx_sphere* spheres, size_t n_spheres,
+                                    const atx_material* materials, size_t n_materials,
+                                    const atx_light* lights, size_t n_lights);
+
+/* Camera(fov, near, far, position, direction) + Camera::Resize(w,h) of the
+ * current size: builds projection/view and their inverses on the host with the
+ * reference's evaluation order (Camera.cpp:14-29, :134-159) — primary rays are
+ * then generated in-kernel, bit-identical to Camera::UpdateRayDirection
+ * (Camera.cpp:161-195). Replaces Camera::allocateDevice/freeDevice (:197-220). */
+ATX_API atx_status atx_set_camera(atx_handle h, const float position[3], const float direction[3],
+                                  float fov_degrees, float near_clip, float far_clip);
+
+/* Same, from explicit column-major inverse-projection and inverse-view matrices
+ * (Camera::getInverseProjectionMatrix / getInverseViewMatrix, Camera.h:49-50). */
+ATX_API atx_status atx_set_camera_matrices(atx_handle h, const float position[3],
+                                           const float inv_projection[16], const float inv_view[16]);
+
+/* Renderer::setSettings, Renderer.h:28; Settings = Scene.h:49-56. */
+ATX_API atx_status atx_set_settings(atx_handle h, int accumulation, int sky_light, int max_bounces);
+
+/* Tuning knobs that never change results (parity tests sweep them). */
+enum {
+    ATX_TUNE_CHUNK_SPHERES = 1 /* spheres per shared-memory chunk; 0 = automatic. Forces the
+                                  chunked (double-buffered) staging path when < n_spheres. */
+};
+ATX_API atx_status atx_set_tuning(atx_handle h, int key, int64_t value);
+
+/* Renderer::resetFrameIndex, Renderer.h:30 (the next render zeroes the
+ * accumulation buffer, Renderer.cu:181-182). */
+ATX_API atx_status atx_reset(atx_handle h);
+
+/* Current frameIndex (1 after a reset; Renderer.cu:245-248). */
+ATX_API atx_status atx_frame_index(atx_handle h, uint32_t* out);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* n_frames x { Renderer::Render, Renderer.cu:173-249 } in ONE launch: frames
+ * frameIndex .. frameIndex+n_frames-1 are accumulated in registers in the
+ * reference's order (so the float4 sums are bit-identical to n_frames
+ * sequential reference frames), one 16 B read + one 16 B write per pixel.
+ * frameIndex advances by n_frames (or stays 1 when accumulation is off, :245-248).
+ * Asynchronous on the handle's stream; atx_sync or any atx_read_* waits. */
+ATX_API atx_status atx_render(atx_handle h, uint32_t n_frames, int variant);
+
+/* Multi-GPU spp split: accumulate frame indices
+ * first, first+stride, ... (n_frames of them) WITHOUT touching frameIndex.
+ * zero_first != 0 starts from a zeroed accumulation buffer. */
+ATX_API atx_status atx_render_frames(atx_handle h, uint32_t first_frame, uint32_t n_frames,
+                                     uint32_t frame_stride, int zero_first, int variant);
+
+/* Wait for everything queued on the handle's stream. */
+ATX_API atx_status atx_sync(atx_handle h);
+
+/* Device time (ms, CUDA events on the handle's stream) of the last atx_render*
+ * call's kernels. Synchronises. */
+ATX_API atx_status atx_last_render_ms(atx_handle h, float* out_ms);
+
+/* ---- results ------------------------------------------------------------- */
+
+/* float4 accumulation buffer (Renderer::d_accumulation_, Renderer.h:55):
+ * width*height*4 floats, row-major x + y*width, .w = exact sample count. */
+ATX_API atx_status atx_read_accum(atx_handle h, float* dst);
+
+/* Overwrite the accumulation buffer from host data and set frameIndex — the
+ * resumable-render state. */
+ATX_API atx_status atx_write_accum(atx_handle h, const float* src, uint32_t next_frame_index);
+
+/* RGBA8 image as Renderer::Render leaves it in h_imageData_ (Renderer.cu:165-168,
+ * :240; packing colorUtils::vec4ToRGBA, Renderer.h:70-78): clamp(acc/divisor,0,1),
+ * truncating, alpha from acc.w. divisor = 0 means "frameIndex of the last
+ * rendered frame". */
+ATX_API atx_status atx_read_rgba8(atx_handle h, uint32_t* dst, uint32_t divisor);
+
+/* Parity/debug: index of the closest sphere hit by each primary ray (-1 = miss),
+ * via the same intersection code as the path loop (Renderer::traceRay,
+ * Renderer.cu:251-285). width*height int32. */
+ATX_API atx_status atx_read_hit_ids(atx_handle h, int32_t* dst);
+
+/* Parity/debug: the in-kernel primary ray directions, width*height*3 floats
+ * (the table Camera::getRayDirection returns, Camera.h:60). */
+ATX_API atx_status atx_read_ray_directions(atx_handle h, float* dst);
+
+/* Exact device counters since the last atx_reset_counters. */
+ATX_API atx_status atx_get_counters(atx_handle h, atx_counters* out);
+ATX_API atx_status atx_reset_counters(atx_handle h);
+
+/* Raw device pointers for interop (torch tensors, NCCL, peer access). */
+ATX_API atx_status atx_accum_device_ptr(atx_handle h, void** out);
+ATX_API atx_status atx_stream(atx_handle h, void** out_cuda_stream);
+
+/* ---- multi-GPU: spp split + sum of accumulation buffers over NVLink ------- */
+
+/* 128-byte NCCL unique id (rank 0 creates, the host broadcasts it). */
+ATX_API atx_status atx_comm_unique_id(uint8_t id[128]);
+ATX_API atx_status atx_comm_init_rank(atx_handle h, int n_ranks, int rank, const uint8_t id[128]);
+ATX_API atx_status atx_comm_destroy(atx_handle h);
+
+/* ncclAllReduce(float32, sum) of the accumulation buffer in place, on the
+ * handle's stream (count = 4*width*height). .w sums to the exact total spp. */
+ATX_API atx_status atx_allreduce_accum(atx_handle h);
+
+/* ---- host math helpers ------------------------------------------------------
+ * CPU-side pieces of the reference's HOST API (they run on the CPU in the reference
+ * too), compiled inside this library so the caller's compiler flags cannot perturb
+ * the exact glm evaluation order parity depends on. Used by the header-only C++
+ * mirror (include/ataraxia/*.h). None of them is on the render path. Matrices are
+ * column-major float[16] (glm::mat4 layout). */
+
+/* Camera::UpdateProjectionMatrix + UpdateViewMatrix, Camera.cpp:134-159. Any output
+ * pointer may be NULL. */
+ATX_API atx_status atx_host_camera_matrices(const float position[3], const float direction[3], float fov_degrees,
+                                            float near_clip, float far_clip, uint32_t width, uint32_t height,
+                                            float projection[16], float view[16],
+                                            float inv_projection[16], float inv_view[16]);
+
+/* Camera::UpdateRayDirection, Camera.cpp:161-195 (multithreaded like the reference):
+ * the table Camera::getRayDirection() exposes. out = width*height*3 floats. */
+ATX_API atx_status atx_host_ray_directions(const float inv_projection[16], const float inv_view[16],
+                                           uint32_t width, uint32_t height, float* out);
+
+/* SceneNode::updateGlobalTransform, SceneNode.cpp:42-59: local = T * R * S,
+ * global = parent * local. rotation is (x, y, z, w). */
+ATX_API atx_status atx_host_node_transform(const float parent[16], const float position[3],
+                                           const float rotation_xyzw[4], const float scale[3],
+                                           float local[16], float global[16]);
+
+/* out = a * b in glm's column-by-column order (type_mat4x4.inl mul4x4), e.g. the
+ * non-dirty branch "m_globalTransform = parentTransform * m_localTransform",
+ * SceneNode.cpp:51-54. */
+ATX_API atx_status atx_host_mat4_mul(const float a[16], const float b[16], float out[16]);
+
+/* One sphere of Renderer::traverseSceneGraph, Renderer.cu:77-88. */
+ATX_API atx_status atx_host_transform_sphere(const float global[16], const atx_sphere* in, atx_sphere* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATARAXIA_B200_H */
