@@ -1,7 +1,7 @@
 // atx_device.cuh — device data layout and the per-path building blocks shared by
 // the megakernel and the wavefront kernels. Every function cites the reference
 // code it restates (file:line under /root/reference) and follows the op sequence of
-// the reference's own sm_100a PTX, using only atx_exact.cuh ops.
+// the reference's own sm_100a SASS, using only atx_exact.cuh ops.
 #pragma once
 #include "atx_exact.cuh"
 
@@ -10,7 +10,7 @@ namespace atxk
 
 // ---------------------------------------------------------------------------
 // Scene records in HBM, written once per upload by pack_scene_kernel.
-//   spheres : float4 (cx, cy, cz, r*r)      SoA-of-float4, one LDS.128 / LDG.128 per test
+//   spheres : float4 (cx, cy, cz, radius)   SoA-of-float4, one LDS.128 / LDG.128 per test
 //   sphMat  : int32 material index          read only for the winning sphere
 //   mats    : 6 x float4 per material       everything the shading needs, including the
 //                                           per-material subexpressions the reference
@@ -94,14 +94,23 @@ ATX_DEV V3 primary_direction(const CameraParams& c, uint32_t x, uint32_t y, uint
 
 // ---------------------------------------------------------------------------
 // Ray / sphere loop, Renderer::traceRay (Renderer.cu:251-285).
-// Reference per sphere: oc = o - c; b = 2*dot(oc,d); c = dot(oc,oc) - r*r;
-// disc = b*b - 4*a*c (mul, mul, sub — not contracted); if disc < 0 skip.
-// The miss path here tests the sign of hb*hb - a*c' (hb = dot(oc,d), b = hb + hb):
-// b*b = 4*hb*hb and (4a)*c' = 4*(a*c') are exact power-of-two scalings, so the two
-// discriminants have the same sign; the only exceptions (flush-to-zero of one but
-// not the other) land in the not-less-than-zero side here and are re-decided below
-// with the reference's literal sequence, so decisions are identical. 13 FP
-// instructions per missed sphere instead of 15, r*r precomputed by the same mul.
+//
+// Ground truth is the reference's sm_100a SASS, not its PTX: the PTX carries
+// mul/add/sub without ".rn", which ptxas is allowed to (and does) contract. Per
+// sphere the reference executes
+//     oc = o - c                      3 FADD
+//     hb = fma(oc.z,d.z, fma(oc.x,d.x, oc.y*d.y))          FMUL + 2 FFMA
+//     q  = fma(oc.z,oc.z, fma(oc.x,oc.x, oc.y*oc.y))       FMUL + 2 FFMA
+//     c' = fma(-r, r, q)              FFMA   (r*r is NOT rounded separately)
+//     b  = hb + hb                    FADD
+//     disc = fma(b, b, -(a4*c'))      FMUL + FFMA
+//     if disc < 0 skip
+// The miss path here tests sign(fma(hb,hb, -(a*c'))) instead: b*b = 4*hb*hb exactly
+// and (4a)*c' = 4*(a*c') exactly (power-of-two scalings commute with rounding), so
+// disc = 4 * fma(hb,hb,-(a*c')) and the signs agree; the only exceptions (one value
+// flushed to zero, the other not) land on the not-less-than-zero side here and are
+// re-decided below with the reference's literal sequence. 12 FP instructions per
+// missed sphere instead of the reference's 13.
 // ---------------------------------------------------------------------------
 struct RayConst
 {
@@ -119,6 +128,7 @@ ATX_DEV RayConst ray_constants(float dx, float dy, float dz)
     return k;
 }
 
+// sp = (cx, cy, cz, radius)
 ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
                               const RayConst& k, float& tmin, int& closest)
 {
@@ -126,13 +136,13 @@ ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, fl
     const float ocy = fsub(oy, sp.y);
     const float ocz = fsub(oz, sp.z);
     const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
-    const float cc = fsub(fdot3(ocx, ocy, ocz, ocx, ocy, ocz), sp.w);
-    const float pre = fsub(fmul(hb, hb), fmul(k.a, cc));
+    const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
+    const float pre = ffma(hb, hb, fneg(fmul(k.a, cc)));
     if (!(pre < 0.0f))
     {
-        // literal reference sequence (Renderer.cu:263-278 as compiled)
+        // literal reference sequence (kernelRender SASS, Renderer.cu:263-278)
         const float b = fadd(hb, hb);
-        const float disc = fsub(fmul(b, b), fmul(k.a4, cc));
+        const float disc = ffma(b, b, fneg(fmul(k.a4, cc)));
         if (!(disc < 0.0f))
         {
             const float sq = fsqrt_approx(disc);
@@ -218,7 +228,7 @@ ATX_DEV V3 cook_torrance(const float4 m0, const float4 m1, const float4 m2, cons
 }
 
 // Tangent frame + combination shared by both samplers (BRDF.cu:83-92 / :107-116):
-// T from the larger of |N.x|,|N.y|; B = cross(N,T) (mul, mul, sub); result = x*T + y*B + z*N
+// T from the larger of |N.x|,|N.y|; B = cross(N,T) (fma(a,b,-(c*d)) as ptxas contracts it); result = x*T + y*B + z*N
 // as fma(z, N, fma(x, T, y*B)).
 ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
 {
@@ -237,9 +247,10 @@ ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
         Ty = fdiv_approx(fneg(N.z), s);
         Tz = fdiv_approx(N.y, s);
     }
-    const float Bx = fsub(fmul(Tz, N.y), fmul(Ty, N.z));
-    const float By = fsub(fmul(Tx, N.z), fmul(Tz, N.x));
-    const float Bz = fsub(fmul(Ty, N.x), fmul(Tx, N.y));
+    // cross(N, T): ptxas fuses the first product of each component (sampler SASS 0x380-0x3d0)
+    const float Bx = ffma(N.y, Tz, fneg(fmul(Ty, N.z)));
+    const float By = ffma(Tx, N.z, fneg(fmul(N.x, Tz)));
+    const float Bz = ffma(N.x, Ty, fneg(fmul(N.y, Tx)));
     return { ffma(z, N.x, ffma(x, Tx, fmul(y, Bx))),
              ffma(z, N.y, ffma(x, Ty, fmul(y, By))),
              ffma(z, N.z, ffma(x, Tz, fmul(y, Bz))) };
@@ -265,7 +276,7 @@ ATX_DEV V3 sample_ggx(const V3 N, float ggxT, uint32_t& seed)
     const float u1 = pcg_float(seed);
     const float u2 = pcg_float(seed);
     const float cosT = fsqrt_approx(fdiv_approx(fsub(1.0f, u1), ffma(ggxT, u1, 1.0f)));
-    const float sinT = fsqrt_approx(fsub(1.0f, fmul(cosT, cosT)));
+    const float sinT = fsqrt_approx(ffma(fneg(cosT), cosT, 1.0f)); // 1 - cos^2, contracted by ptxas (SASS 0x2d0)
     const float phi = fmul(u2, 6.28318548f);
     const float x = fmul(sinT, fcos_approx(phi));
     const float y = fmul(sinT, fsin_approx(phi));

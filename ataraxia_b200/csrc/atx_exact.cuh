@@ -8,7 +8,9 @@
 // mul+add pairs nvcc contracts into fma. The kernels therefore never write
 // `a*b+c`; every floating-point operation is one of the functions below, each
 // exactly one PTX instruction that the compiler can neither contract, split nor
-// reassociate. The op sequences that use them follow the reference's sm_100a PTX
+// reassociate. Ground truth for the op sequences is the reference's sm_100a SASS
+// (cuobjdump of oracle/_ref/ref_headless), not its PTX: the PTX carries mul/add/sub
+// without ".rn", which ptxas may — and in five places does — contract further
 // (listed function by function in DESIGN.md §4).
 //
 // Two families:

@@ -33,7 +33,7 @@ __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSp
     {
         const float* s = sphAoS + 5 * i; // Sphere: center[3], radius, id (20 B)
         const float r = s[3];
-        spheres[i] = make_float4(s[0], s[1], s[2], fmul(r, r)); // Renderer.cu:264 radius*radius
+        spheres[i] = make_float4(s[0], s[1], s[2], r);
         int32_t id = reinterpret_cast<const int32_t*>(s)[4];
         if (static_cast<uint32_t>(id) >= nMaterials) // Renderer.cu:30-37
             id = 0;
@@ -264,10 +264,11 @@ __global__ void __launch_bounds__(256, 2) megakernel(const RenderParams p)
                 const V3 L = { dx, dy, dz };
                 const V3 s = cook_torrance(m0, m1, m2, m3, N, V, L);
                 const float4 le = __ldg(p.lights + kLightStride * lightIndex + 1);
-                // color += emission * specular * throughput / pdf(=1)   (Renderer.cu:362-367)
-                cr = fadd(cr, fdiv_approx(fmul(tx, fmul(le.x, s.x)), 1.0f));
-                cg = fadd(cg, fdiv_approx(fmul(ty, fmul(le.y, s.y)), 1.0f));
-                cb = fadd(cb, fdiv_approx(fmul(tz, fmul(le.z, s.z)), 1.0f));
+                // color += emission * specular * throughput / pdf(=1)   (Renderer.cu:362-367): ptxas folds
+                // the division by 1 and contracts the last product into the sum (kernelRender SASS 0x32d0-0x3350)
+                cr = ffma(fmul(le.x, s.x), tx, cr);
+                cg = ffma(fmul(le.y, s.y), ty, cg);
+                cb = ffma(fmul(le.z, s.z), tz, cb);
             }
             doBounce = true;
         }
