@@ -367,6 +367,13 @@ class Renderer:
         check(_capi.lib().atx_last_render_ms(self._h, C.byref(v)))
         return v.value
 
+    def eventRecord(self, slot: int): check(_capi.lib().atx_event_record(self._h, slot))
+
+    def eventElapsedMs(self, begin: int, end: int) -> float:
+        v = C.c_float()
+        check(_capi.lib().atx_event_elapsed_ms(self._h, begin, end, C.byref(v)))
+        return v.value
+
     def setTuning(self, key: int, value: int):
         check(_capi.lib().atx_set_tuning(self._h, key, value))
 

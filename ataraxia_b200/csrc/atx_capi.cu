@@ -112,6 +112,7 @@ struct atx_renderer
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
+    cudaEvent_t evUser[8] = {};
     bool timed = false;
 
     uint32_t width = 0, height = 0;
@@ -259,6 +260,9 @@ atx_status atx_destroy(atx_handle h)
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
+    for (cudaEvent_t e : h->evUser)
+        if (e)
+            cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
     return ATX_OK;
@@ -498,6 +502,30 @@ atx_status atx_last_render_ms(atx_handle h, float* out_ms)
         return fail(ATX_ERR_INVALID, "nothing rendered yet");
     ATX_CUDA(cudaEventSynchronize(h->evStop));
     ATX_CUDA(cudaEventElapsedTime(out_ms, h->evStart, h->evStop));
+    return ATX_OK;
+}
+
+atx_status atx_event_record(atx_handle h, int slot)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (slot < 0 || slot >= 8)
+        return fail(ATX_ERR_INVALID, "event slot out of range");
+    if (!h->evUser[slot])
+        ATX_CUDA(cudaEventCreate(&h->evUser[slot]));
+    ATX_CUDA(cudaEventRecord(h->evUser[slot], h->stream));
+    return ATX_OK;
+}
+
+atx_status atx_event_elapsed_ms(atx_handle h, int slot_begin, int slot_end, float* out_ms)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!out_ms || slot_begin < 0 || slot_begin >= 8 || slot_end < 0 || slot_end >= 8 || !h->evUser[slot_begin] ||
+        !h->evUser[slot_end])
+        return fail(ATX_ERR_INVALID, "bad or unrecorded event slot");
+    ATX_CUDA(cudaEventSynchronize(h->evUser[slot_end]));
+    ATX_CUDA(cudaEventElapsedTime(out_ms, h->evUser[slot_begin], h->evUser[slot_end]));
     return ATX_OK;
 }
 

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+
+Metric (BASELINE.json): Mpaths/s (and Grays/s) at 1920x1080, 8 bounces. A "step" is one pass of the
+hot path over one batch: the full config-2 render (sample scene, 1024 spp) on each GPU. With N GPUs
+every rank renders its own 1024 frame indices of an N*1024-spp image (spp split, weak scaling) and
+the float4 accumulation buffers are summed with one NCCL all-reduce inside the timed step.
+
+ value : whole-job Mpaths/s, scene resident in HBM, device-timed (CUDA events on the renderer's
+         stream, max over ranks), L2 flushed between steps.
+ e2e   : same metric through the public API with HOST buffers: scene upload (pinned host memory),
+         camera, reset, render, RGBA8 read-back to pinned host memory — every step, wall-clock.
+ roofline : FP32 FMA issue (no stage is a dense contraction — no tensor cores): algorithmic flops
+         = 19 per ray-sphere test + 7 per ray, from exact device counters.
+ cpu_baseline : the reference's per-pixel shading compiled for the host (oracle/_ref/libref_cpu.so,
+         kind "reference") or the oracle port, all host threads, bounded sample.
+ --impl reference : times that CPU implementation as its own arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # SMs x FP32 lanes x 2 flop x max SM clock = 74.4
+FLOP_PER_TEST, FLOP_PER_RAY = 19, 7
+
+WORKLOADS = {
+    # name: (description, width, height, spp, bounces)
+    "c2": ("sample-scene-data/scene.json 1920x1080 1024spp 8 bounces", 1920, 1080, 1024, 8),
+    "c3": ("synthetic 256 spheres 16 lights 3840x2160 256spp 8 bounces", 3840, 2160, 256, 8),
+    "c4": ("synthetic 4096 spheres 3840x2160 64spp 8 bounces", 3840, 2160, 64, 8),
+    "c1": ("sample-scene-data/scene.json 1280x720 1spp 5 bounces", 1280, 720, 1, 5),
+}
+
+
+def load_scene(atx, name):
+    if name in ("c1", "c2"):
+        return atx.Utils.importScene(str(ROOT / "tests" / "golden" / "sample_scene.json"))
+    return atx.synthetic.config3() if name == "c3" else atx.synthetic.config4()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(workload, steps, warmup, threads=0, target_seconds=4.0):
+    """The reference's per-pixel path on the host cores: oracle/_ref/libref_cpu.so (reference sources
+    compiled host-side) when present, else the oracle port. Bounded sample of the workload per step."""
+    import ataraxia_b200 as atx
+    from oracle import bindings as ob
+    desc, W, H, spp, bounces = WORKLOADS[workload]
+    if ob.have_reference_cpu():
+        impl, kind = ob.ReferenceCpu(), "reference"
+    else:
+        impl, kind = ob.OraclePort(), "port"
+    cores = impl.hardware_threads()
+    scene = load_scene(atx, workload)
+    s = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
+    s["material"] = np.where((s["material"] < 0) | (s["material"] >= len(scene.materials)), 0, s["material"])
+    m, l = atx.pack_materials(scene.materials), atx.pack_lights(scene.lights)
+    port = ob.OraclePort()
+    rays, _, _ = port.camera(scene.camera.getPosition(), scene.camera.getDirection(), scene.camera.getFov(), 0.1, 100.0, W, H)
+    pos = scene.camera.getPosition()
+    # calibrate: one frame over a thin band, then size the sample to ~target_seconds per step
+    band = max(cores, H // 8)
+    t0 = time.perf_counter()
+    impl.render(s, m, l, pos, rays, 1, 1, 1, bounces, False, rows=(H // 2 - band // 2, H // 2 - band // 2 + band), threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rate = band * W / dt
+    frames = int(max(1, min(spp, target_seconds * rate / (W * H))))
+    rows = (0, H)
+    if frames == 1 and W * H / rate > 2 * target_seconds:   # even one full frame is too slow: band of rows
+        nrows = int(max(cores, min(H, target_seconds * rate / W)))
+        rows = (H // 2 - nrows // 2, H // 2 - nrows // 2 + nrows)
+    paths = (rows[1] - rows[0]) * W * frames
+    times = []
+    for i in range(warmup + steps):
+        acc = np.zeros((H, W, 4), np.float32)
+        t0 = time.perf_counter()
+        impl.render(s, m, l, pos, rays, 1, frames, 1, bounces, False, accum=acc, rows=rows, threads=threads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    sample = f"{W}x{rows[1] - rows[0]} rows of {W}x{H}, {frames} of {spp} spp, {bounces} bounces"
+    return {"value": paths / sec / 1e6, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample,
+            "ms_per_step": sec * 1e3, "paths_per_step": paths}
+
+
+def ref_cuda_baseline(workload, frames=24):
+    """The reference's own CUDA renderer on this GPU (oracle/_ref/ref_headless), one Render() per spp."""
+    from oracle import bindings as ob
+    if not ob.have_ref_headless():
+        return None
+    desc, W, H, spp, bounces = WORKLOADS[workload]
+    if workload in ("c1", "c2"):
+        path = ROOT / "tests" / "golden" / "sample_scene.json"
+    else:
+        return None
+    try:
+        info, _ = ob.run_ref_headless(path, W, H, bounces, False, frames, timeout=300)
+    except Exception as e:  # reported baseline only: never fail the bench on it
+        return {"error": str(e)[:200]}
+    P = W * H
+    return {"kind": "reference-cuda (unmodified Renderer::Render, sm_100a build)", "frames": frames,
+            "median_frame_ms": info["median_frame_ms"], "min_frame_ms": info["min_frame_ms"],
+            "value": P / info["median_frame_ms"] / 1e3, "unit": "Mpaths/s",
+            "note": "end-to-end Render() wall time per 1-spp frame (host ray-table upload + sync + RGBA8 read-back included, as the app runs it)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per step (default: the workload's)")
+    ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference-CUDA legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, W, H, spp, bounces = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = cpu_reference_arm(args.workload, max(args.steps, 1), max(args.warmup, 0))
+        line = {"impl": "reference", "metric": "Mpaths/s", "value": res["value"], "unit": "Mpaths/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "width": W, "height": H, "spp": spp, "max_bounces": bounces},
+                "cpu_baseline": {"value": res["value"], "unit": "Mpaths/s", "cores": res["cores"], "kind": res["kind"],
+                                 "sample": res["sample"]},
+                "e2e": {"value": res["value"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import ataraxia_b200 as atx
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = load_scene(atx, args.workload)
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    r = atx.Renderer(local_rank)
+    r.setSettings(atx.Settings(True, False, bounces))
+    r.onResize(W, H)
+    cam.Resize(W, H)
+    spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
+    mats, lights = atx.pack_materials(scene.materials), atx.pack_lights(scene.lights)
+    r.uploadArrays(spheres, mats, lights)
+    r.setCamera(cam)
+    if world > 1:
+        uid = [atx.Renderer.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        r.commInitRank(world, rank, uid[0])
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        # rank's share of the (world * spp)-spp image: frame indices rank+1, rank+1+world, ...
+        r.eventRecord(0)
+        r.renderFrames(rank + 1, spp, world, zero_first=True)
+        if world > 1:
+            r.allreduceAccum()
+        r.eventRecord(1)
+
+    for _ in range(args.warmup):
+        step()
+    r.sync()
+    r.resetCounters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = []
+    for _ in range(args.steps):
+        flush.fill_(0)            # L2 flush between timed iterations (not inside the event bracket)
+        torch.cuda.synchronize()
+        step()
+        dev_ms.append(r.eventElapsedMs(0, 1))
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop()
+    c = r.counters()
+    total_ms = sum(dev_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        cnt = torch.tensor([c.paths, c.rays, c.sphere_tests], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(cnt)
+        paths, rays, tests = (float(v) for v in cnt.tolist())
+    else:
+        paths, rays, tests = float(c.paths), float(c.rays), float(c.sphere_tests)
+    launches = int(c.launches)
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region -------------------------
+    pin = lambda a: torch.from_numpy(a.view(np.uint8).copy()).pin_memory()  # noqa: E731
+    hs, hm, hl = pin(spheres), pin(mats), pin(lights)
+    host_rgba = torch.empty((H, W), dtype=torch.int32).pin_memory()
+    rgba_np = host_rgba.numpy().view(np.uint32)
+    e2e_steps = max(2, min(args.steps, 3))
+
+    def e2e_step():
+        r.uploadArrays(hs.numpy().view(atx.SPHERE_DTYPE), hm.numpy().view(atx.MATERIAL_DTYPE), hl.numpy().view(atx.LIGHT_DTYPE))
+        r.setCamera(cam)
+        r.renderFrames(rank + 1, spp, world, zero_first=True)
+        if world > 1:
+            r.allreduceAccum()
+        r.getRGBA8(divisor=spp * world, out=rgba_np)   # resolve + D2H; waits for the stream
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_paths = float(W) * H * spp * world * e2e_steps
+
+    if rank == 0:
+        peaks = measured_peaks()
+        flops = FLOP_PER_TEST * tests + FLOP_PER_RAY * rays
+        achieved = flops / (total_ms * 1e-3) / 1e12 / world      # per GPU
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            try:
+                traffic = json.loads(tpath.read_text()).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "Mpaths/s", "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
+                       "spheres": int(len(spheres)), "lights": int(len(lights)), "parallelism": f"spp-split x{world}",
+                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel"},
+            "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
+            "wall_ms_total": wall_ms,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_paths / e2e_s / 1e6, "unit": "Mpaths/s",
+                    "h2d_bytes_per_step": int(spheres.nbytes + mats.nbytes + lights.nbytes + 2 * 64 + 12),
+                    "d2h_bytes_per_step": int(W * H * 4), "steps": e2e_steps},
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP32_PEAK_TFLOPS, "traffic": traffic,
+                         "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm 1965 MHz (MEASURED_PEAKS.json sm_max_mhz); "
+                                        "no tensor-core or HBM bound applies to this kernel",
+                         "algorithmic": "19 flop per ray-sphere test + 7 per ray, exact device counters",
+                         "accum_hbm": {"bytes_per_pixel_per_launch": 16, "gbs": 16.0 * W * H / (total_ms / args.steps * 1e-3) / 1e9,
+                                       "peak_gbs": peaks.get("hbm_gbs")}},
+        }
+        if world == 1 and not args.no_baselines:
+            cb = cpu_reference_arm(args.workload, 1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            rc = ref_cuda_baseline(args.workload)
+            if rc:
+                line["ref_cuda_baseline"] = rc
+            # BASELINE metric part 2: ms/frame at 1 spp (config 1), end to end through Renderer::Render
+            s1 = load_scene(atx, "c1")
+            cam1 = atx.Camera(s1.camera.getFov(), 0.1, 100.0, s1.camera.getPosition(), s1.camera.getDirection())
+            r1 = atx.Renderer(local_rank)
+            r1.setSettings(atx.Settings(True, False, 5))
+            r1.onResize(1280, 720); cam1.Resize(1280, 720)
+            for _ in range(5):
+                r1.Render(cam1, s1)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                r1.Render(cam1, s1)
+            line["ms_per_frame_1spp"] = {"value": (time.perf_counter() - t0) / 50 * 1e3, "unit": "ms",
+                                         "config": WORKLOADS["c1"][0], "kernel_ms": r1.lastRenderMs(),
+                                         "includes": "Render(): camera, launch, RGBA8 read-back to host"}
+            r1.close()
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

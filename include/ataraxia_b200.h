@@ -171,6 +171,11 @@ ATX_API atx_status atx_sync(atx_handle h);
  * call's kernels. Synchronises. */
 ATX_API atx_status atx_last_render_ms(atx_handle h, float* out_ms);
 
+/* General-purpose device timers on the handle's stream (CUDA events), e.g. to bracket
+ * render + all-reduce. slot in [0, 8). elapsed synchronises on the later event. */
+ATX_API atx_status atx_event_record(atx_handle h, int slot);
+ATX_API atx_status atx_event_elapsed_ms(atx_handle h, int slot_begin, int slot_end, float* out_ms);
+
 /* ---- results ------------------------------------------------------------- */
 
 /* float4 accumulation buffer (Renderer::d_accumulation_, Renderer.h:55):
