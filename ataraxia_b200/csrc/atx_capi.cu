@@ -135,6 +135,8 @@ struct atx_renderer
     uint32_t frameIndex = 1;
     uint32_t lastFrame = 1;     // frameIndex of the last rendered frame (display divisor)
     uint32_t chunkOverride = 0; // tuning: force the shared-memory chunk size (spheres)
+    int megaKind = 0;           // tuning: 0 = by sphere count, 1 = while-while, 2 = two-slot packed
+    uint32_t traceRounds = 2;   // tuning: closest-hit rounds per shading phase (while-while form)
     uint64_t launches = 0;
 
     ncclComm_t comm = nullptr;
@@ -172,6 +174,7 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
     else if (h->nS > fit)
         chunk = fit / 2; // double-buffered
     p.chunkSpheres = chunk ? chunk : 1;
+    p.traceRounds = h->traceRounds;
     const atx::mat4& ip = h->cam.invProj;
     const atx::mat4& iv = h->cam.invView;
     for (int i = 0; i < 4; i++)
@@ -386,6 +389,16 @@ atx_status atx_set_tuning(atx_handle h, int key, int64_t value)
             return fail(ATX_ERR_INVALID, "chunk_spheres must be in [0, 7000] (0 = automatic)");
         h->chunkOverride = static_cast<uint32_t>(value);
         return ATX_OK;
+    case ATX_TUNE_MEGA_KIND:
+        if (value < 0 || value > 2)
+            return fail(ATX_ERR_INVALID, "mega_kind must be 0 (auto), 1 (while-while) or 2 (two-slot packed)");
+        h->megaKind = static_cast<int>(value);
+        return ATX_OK;
+    case ATX_TUNE_TRACE_ROUNDS:
+        if (value < 1 || value > 64)
+            return fail(ATX_ERR_INVALID, "trace_rounds must be in [1, 64]");
+        h->traceRounds = static_cast<uint32_t>(value);
+        return ATX_OK;
     default:
         return fail(ATX_ERR_INVALID, "unknown tuning key %d", key);
     }
@@ -425,7 +438,7 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.rgbaDivisor = rgbaDivisor;
     if (atx_launch::megakernel_smem_bytes(p) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
         return fail(ATX_ERR_INVALID, "shared-memory plan exceeds the device limit");
-    ATX_CUDA(atx_launch::render_mega(p, h->stream));
+    ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->stream));
     h->launches++;
     return ATX_OK;
 }

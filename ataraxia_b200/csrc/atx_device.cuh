@@ -10,7 +10,9 @@ namespace atxk
 
 // ---------------------------------------------------------------------------
 // Scene records in HBM, written once per upload by pack_scene_kernel.
-//   spheres : float4 (cx, cy, cz, radius)   SoA-of-float4, one LDS.128 / LDG.128 per test
+//   spheres : float4 (-cx, -cy, -cz, radius) one LDS.128 per test. The centre is stored
+//                                           NEGATED: o - c == o + (-c) bit for bit, and the
+//                                           packed f32x2 ops have add but no subtract form
 //   sphMat  : int32 material index          read only for the winning sphere
 //   mats    : 6 x float4 per material       everything the shading needs, including the
 //                                           per-material subexpressions the reference
@@ -49,6 +51,7 @@ struct RenderParams
     uint32_t rgbaDivisor;   // frameIndex used for the display divide (Renderer.cu:166)
     uint32_t nSpheres, nMaterials, nLights;
     uint32_t chunkSpheres;  // spheres per shared-memory chunk (>= nSpheres: staged once)
+    uint32_t traceRounds;   // while-while kernel: closest-hit rounds before the shading phase
     const float4* spheres;
     const int32_t* sphMat;
     const float4* mats;
@@ -128,46 +131,108 @@ ATX_DEV RayConst ray_constants(float dx, float dy, float dz)
     return k;
 }
 
-// sp = (cx, cy, cz, radius)
-ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
-                              const RayConst& k, float& tmin, int& closest)
+// The reference's literal sequence for one sphere whose line test did not rule it out
+// (kernelRender SASS, Renderer.cu:263-278). sp = (-cx, -cy, -cz, radius).
+ATX_DEV void exact_tail(float hb, float cc, int index, const RayConst& k, float& tmin, int& closest)
 {
-    const float ocx = fsub(ox, sp.x);
-    const float ocy = fsub(oy, sp.y);
-    const float ocz = fsub(oz, sp.z);
-    const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
-    const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
-    const float pre = ffma(hb, hb, fneg(fmul(k.a, cc)));
-    if (!(pre < 0.0f))
+    const float b = fadd(hb, hb);
+    const float disc = ffma(b, b, fneg(fmul(k.a4, cc)));
+    if (!(disc < 0.0f))
     {
-        // literal reference sequence (kernelRender SASS, Renderer.cu:263-278)
-        const float b = fadd(hb, hb);
-        const float disc = ffma(b, b, fneg(fmul(k.a4, cc)));
-        if (!(disc < 0.0f))
+        const float sq = fsqrt_approx(disc);
+        const float t0 = fdiv_approx(fsub(fneg(b), sq), k.a2);
+        const float t1 = fdiv_approx(fsub(sq, b), k.a2);
+        const float t = t0 < t1 ? t0 : t1;
+        if (t > 0.0f && t < tmin)
         {
-            const float sq = fsqrt_approx(disc);
-            const float t0 = fdiv_approx(fsub(fneg(b), sq), k.a2);
-            const float t1 = fdiv_approx(fsub(sq, b), k.a2);
-            const float t = t0 < t1 ? t0 : t1;
-            if (t > 0.0f && t < tmin)
-            {
-                tmin = t;
-                closest = index;
-            }
+            tmin = t;
+            closest = index;
         }
     }
 }
 
+// full test of one sphere from scratch (candidate resolution of the packed loop)
+ATX_DEV void exact_test(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
+                        const RayConst& k, float& tmin, int& closest)
+{
+    const float ocx = fadd(ox, sp.x);
+    const float ocy = fadd(oy, sp.y);
+    const float ocz = fadd(oz, sp.z);
+    const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
+    const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
+    exact_tail(hb, cc, index, k, tmin, closest);
+}
+
+// scalar test with the cheap line filter in front (small scenes, debug kernels)
+ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
+                              const RayConst& k, float& tmin, int& closest)
+{
+    const float ocx = fadd(ox, sp.x);
+    const float ocy = fadd(oy, sp.y);
+    const float ocz = fadd(oz, sp.z);
+    const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
+    const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
+    const float pre = ffma(hb, hb, fneg(fmul(k.a, cc)));
+    if (!(pre < 0.0f))
+        exact_tail(hb, cc, index, k, tmin, closest);
+}
+
+// ---------------------------------------------------------------------------
+// Packed line filter: TWO rays (the two path slots of a thread) against one sphere
+// per step, every op an f32x2 instruction with the sphere as the broadcast operand.
+//
+//   oc  = o + (-c)                               3 FADD2
+//   hb  = fma(oc.z,d.z, fma(oc.x,d.x, oc.y*d.y))  FMUL2 + 2 FFMA2
+//   q   = fma(oc.z,oc.z, fma(oc.x,oc.x, oc.y^2))  FMUL2 + 2 FFMA2
+//   cc  = fma(-r, r, q)                          2 scalar FFMA (FFMA2 has no negate modifier)
+//   m   = fma(cc, -a, 2^-100)                    FFMA2
+//   pre = fma(hb, hb, m)                         FFMA2
+//   mask = (mask << 1) | signbit(pre)            2 SHF (ALU pipe)
+//
+// = 1 LDS.128 + 11 packed + 2 scalar FP + 2 SHF = 16 issue slots for two tests, while
+// the FMA pipe is busy 24 cycles: the loop is bound by the FP32 pipe (19 algorithmic
+// flop per 12 pipe-cycles -> 0.79 of peak at full lanes), not by the issue port.
+//
+// The sign of pre decides "the line misses the sphere": hb, cc are bit-identical to the
+// scalar sequence above and pre >= fma(hb,hb,-(a*cc)) (the +2^-100 only matters when
+// |a*cc| < 2^-76, where it keeps the -0/flush cases of the reference's
+// disc = fma(b,b,-(4a*cc)) on the candidate side). A clear sign bit makes the sphere a
+// candidate; candidates are re-decided by exact_test in ascending index order, so the
+// result (tmin, closest) is exactly Renderer::traceRay's.
+// ---------------------------------------------------------------------------
+struct RayPair
+{
+    f32x2 ox, oy, oz, dx, dy, dz;
+    f32x2 na; // (-a0, -a1), a = dot(d,d)
+};
+
+ATX_DEV void filter_sphere(const float4 sp, const RayPair& r, uint32_t& m0, uint32_t& m1)
+{
+    const f32x2 ocx = fadd2(r.ox, pk2(sp.x, sp.x));
+    const f32x2 ocy = fadd2(r.oy, pk2(sp.y, sp.y));
+    const f32x2 ocz = fadd2(r.oz, pk2(sp.z, sp.z));
+    const f32x2 hb = ffma2(ocz, r.dz, ffma2(ocx, r.dx, fmul2(ocy, r.dy)));
+    const f32x2 q = ffma2(ocz, ocz, ffma2(ocx, ocx, fmul2(ocy, ocy)));
+    const float nr = fneg(sp.w);
+    const f32x2 cc = pk2(ffma(nr, sp.w, lo2(q)), ffma(nr, sp.w, hi2(q)));
+    const float tiny = 7.888609052210118e-31f; // 2^-100
+    const f32x2 m = ffma2(cc, r.na, pk2(tiny, tiny));
+    const f32x2 pre = ffma2(hb, hb, m);
+    m0 = shift_in_sign(m0, lo2(pre));
+    m1 = shift_in_sign(m1, hi2(pre));
+}
+
 // Renderer::rayHit (Renderer.cu:396-409): p = (o - c) + d*t (fma); n = p * rsqrt(dot(p,p)); wp = p + c
+// with sp = (-cx, -cy, -cz, r): o - c == o + (-c) and p + c == p - (-c) exactly.
 ATX_DEV void hit_record(const float4 sp, float ox, float oy, float oz, float dx, float dy, float dz, float t,
                         V3& wp, V3& n)
 {
-    const float px = ffma(t, dx, fsub(ox, sp.x));
-    const float py = ffma(t, dy, fsub(oy, sp.y));
-    const float pz = ffma(t, dz, fsub(oz, sp.z));
+    const float px = ffma(t, dx, fadd(ox, sp.x));
+    const float py = ffma(t, dy, fadd(oy, sp.y));
+    const float pz = ffma(t, dz, fadd(oz, sp.z));
     const float inv = frsqrt_approx(fdot3(px, py, pz, px, py, pz));
     n = { fmul(px, inv), fmul(py, inv), fmul(pz, inv) };
-    wp = { fadd(px, sp.x), fadd(py, sp.y), fadd(pz, sp.z) };
+    wp = { fsub(px, sp.x), fsub(py, sp.y), fsub(pz, sp.z) };
 }
 
 // ---------------------------------------------------------------------------
@@ -297,6 +362,137 @@ ATX_DEV uint32_t pack_rgba8(const float4 acc, float divisor)
         u[i] = f32_to_u32_rz_ftz(fmul(v, 255.0f)) & 0xFFu;
     }
     return (u[3] << 24) | (u[2] << 16) | (u[1] << 8) | u[0];
+}
+
+// ---------------------------------------------------------------------------
+// One path of Renderer::perPixel (Renderer.cu:287-387), cut at its two traceRay calls
+// so that every kernel variant (while-while, two-slot packed, wavefront) runs the same
+// code between traces: path_begin -> [trace] -> path_hit -> [shadow trace] ->
+// path_shadow -> path_bounce -> [trace] ... The functions return what the caller must
+// do next; none of them loops.
+// ---------------------------------------------------------------------------
+struct PathState
+{
+    float ox, oy, oz, dx, dy, dz; // ray in flight
+    float cr, cg, cb;             // color
+    float tx, ty, tz;             // throughput
+    uint32_t seed;
+    int bounce;
+    // carried from the closest-hit half to the shadow half of a bounce
+    V3 N, V;
+    float dist2;
+    int matIndex;
+    uint32_t lightIndex;
+};
+
+ATX_DEV void path_begin(PathState& s, const float camPos[3], const V3 d0, uint32_t pixel, uint32_t frame)
+{
+    s.ox = camPos[0]; s.oy = camPos[1]; s.oz = camPos[2];
+    s.dx = d0.x; s.dy = d0.y; s.dz = d0.z;
+    s.cr = s.cg = s.cb = 0.0f;
+    s.tx = s.ty = s.tz = 1.0f;
+    s.seed = pixel * frame; // Renderer.cu:300-301 (bounce 0 adds 0, :306)
+    s.bounce = 0;
+}
+
+// closest-hit ray missed everything (Renderer.cu:309-318): the path ends
+ATX_DEV void path_miss(const RenderParams& p, PathState& s)
+{
+    if (p.skyLight)
+    {
+        s.cr = ffma(s.tx, 0.6f, s.cr);
+        s.cg = ffma(s.ty, 0.7f, s.cg);
+        s.cb = ffma(s.tz, 0.9f, s.cb);
+    }
+}
+
+// closest-hit ray hit sphere `closest` at `t` (Renderer.cu:320-349). sp = that sphere's record.
+// Returns true when a shadow ray is now in flight (s.o/s.d), false when there are no lights
+// (the caller goes straight to path_bounce).
+ATX_DEV bool path_hit(const RenderParams& p, PathState& s, const float4 sp, int closest, float t)
+{
+    V3 wp;
+    hit_record(sp, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, t, wp, s.N);
+    s.matIndex = __ldg(p.sphMat + closest);
+    const float4 m4 = __ldg(p.mats + kMatStride * s.matIndex + 4);
+    if (m4.w > 0.0f) // emission (Renderer.cu:329-333)
+    {
+        s.cr = ffma(s.tx, m4.x, s.cr);
+        s.cg = ffma(s.ty, m4.y, s.cg);
+        s.cb = ffma(s.tz, m4.z, s.cb);
+    }
+    // next origin == shadow origin: pos + N*1e-4 (Renderer.cu:348, :372), an fma
+    const float nox = ffma(s.N.x, 0.0001f, wp.x);
+    const float noy = ffma(s.N.y, 0.0001f, wp.y);
+    const float noz = ffma(s.N.z, 0.0001f, wp.z);
+    bool shadow = false;
+    if (p.nLights > 0)
+    {
+        // light pick reuses the un-advanced seed (Renderer.cu:340)
+        s.lightIndex = pcg_hash(s.seed) % p.nLights;
+        const float4 lp = __ldg(p.lights + kLightStride * s.lightIndex);
+        const float lx = fsub(lp.x, wp.x), ly = fsub(lp.y, wp.y), lz = fsub(lp.z, wp.z);
+        s.dist2 = fdot3(lx, ly, lz, lx, ly, lz);
+        const float inv = frsqrt_approx(s.dist2);
+        s.V = { fsub(0.0f, s.dx), fsub(0.0f, s.dy), fsub(0.0f, s.dz) }; // V = -ray.direction (Renderer.cu:359)
+        s.dx = fmul(lx, inv); s.dy = fmul(inv, ly); s.dz = fmul(inv, lz);
+        shadow = true;
+    }
+    s.ox = nox; s.oy = noy; s.oz = noz;
+    return shadow;
+}
+
+// shadow ray result (Renderer.cu:351-368): occluded iff t > 0 && t*t < dist2
+ATX_DEV void path_shadow(const RenderParams& p, PathState& s, int closest, float tmin)
+{
+    const float ts = closest < 0 ? -1.0f : tmin;
+    if (!(ts > 0.0f && fmul(ts, ts) < s.dist2))
+    {
+        const float4 m0 = __ldg(p.mats + kMatStride * s.matIndex + 0);
+        const float4 m1 = __ldg(p.mats + kMatStride * s.matIndex + 1);
+        const float4 m2 = __ldg(p.mats + kMatStride * s.matIndex + 2);
+        const float4 m3 = __ldg(p.mats + kMatStride * s.matIndex + 3);
+        const V3 L = { s.dx, s.dy, s.dz };
+        const V3 c = cook_torrance(m0, m1, m2, m3, s.N, s.V, L);
+        const float4 le = __ldg(p.lights + kLightStride * s.lightIndex + 1);
+        // color += emission * specular * throughput / pdf(=1)   (Renderer.cu:362-367): ptxas folds
+        // the division by 1 and contracts the last product into the sum (kernelRender SASS 0x32d0-0x3350)
+        s.cr = ffma(fmul(le.x, c.x), s.tx, s.cr);
+        s.cg = ffma(fmul(le.y, c.y), s.ty, s.cg);
+        s.cb = ffma(fmul(le.z, c.z), s.tz, s.cb);
+    }
+}
+
+// throughput, Russian roulette, next direction (Renderer.cu:371-384). Returns true when the
+// path ends (roulette or bounce limit); otherwise the next closest-hit ray is in s.o/s.d.
+ATX_DEV bool path_bounce(const RenderParams& p, PathState& s)
+{
+    const float4 m0 = __ldg(p.mats + kMatStride * s.matIndex + 0);
+    const float4 m1 = __ldg(p.mats + kMatStride * s.matIndex + 1);
+    s.tx = fmul(s.tx, m0.x); s.ty = fmul(s.ty, m0.y); s.tz = fmul(s.tz, m0.z);
+    const float len = fsqrt_approx(fdot3(s.tx, s.ty, s.tz, s.tx, s.ty, s.tz));
+    const float pr = fmax_(fmin_(len, 1.0f), 0.1f);
+    if (pcg_float(s.seed) > pr)
+        return true;
+    s.tx = fdiv_approx(s.tx, pr); s.ty = fdiv_approx(s.ty, pr); s.tz = fdiv_approx(s.tz, pr);
+    V3 nd;
+    if (m1.w > 0.0f)
+        nd = sample_ggx(s.N, __ldg(p.mats + kMatStride * s.matIndex + 5).x, s.seed);
+    else
+        nd = sample_cosine(s.N, s.seed);
+    s.dx = nd.x; s.dy = nd.y; s.dz = nd.z;
+    s.bounce++;
+    if (s.bounce >= p.maxBounces)
+        return true;
+    s.seed += static_cast<uint32_t>(s.bounce); // Renderer.cu:306
+    return false;
+}
+
+// accumulation[p] += vec4(color, 1)   (Renderer.cu:165, :386)
+ATX_DEV void accumulate_sample(float4& acc, const PathState& s)
+{
+    acc.x = fadd(s.cr, acc.x); acc.y = fadd(s.cg, acc.y); acc.z = fadd(s.cb, acc.z);
+    acc.w = fadd(acc.w, 1.0f);
 }
 
 } // namespace atxk

@@ -50,6 +50,29 @@ ATX_DEV uint32_t f32_to_u32_rz_ftz(float a) { uint32_t r; asm("cvt.rzi.ftz.u32.f
 ATX_DEV bool flt(float a, float b) { int r; asm("{ .reg .pred p; setp.lt.ftz.f32 p, %1, %2; selp.s32 %0, 1, 0, p; }" : "=r"(r) : "f"(a), "f"(b)); return r != 0; }
 ATX_DEV bool fgt(float a, float b) { int r; asm("{ .reg .pred p; setp.gt.ftz.f32 p, %1, %2; selp.s32 %0, 1, 0, p; }" : "=r"(r) : "f"(a), "f"(b)); return r != 0; }
 
+// ---- packed pairs (sm_100 f32x2: FADD2 / FMUL2 / FFMA2) --------------------------
+// Two independent fp32 lanes in one 64-bit register, each rounded exactly like the
+// scalar .rn.ftz op, so a packed op is bit-identical to two scalar ops. One issue slot
+// per two flops-pairs: the FMA pipe keeps its 128 lane-ops/clk/SM while the issue port
+// has room for the loads, shifts and branches of the sphere loop (measured with
+// tools/ubench_fp32.cu: ffma 122, ffma2 127 lane-ops/clk/SM at half the issue slots).
+// ptxas turns pk2(x, x) into a scalar-broadcast operand (Rn.F32), so uniform operands
+// cost no extra registers.
+typedef unsigned long long f32x2;
+ATX_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+ATX_DEV float lo2(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+ATX_DEV float hi2(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+ATX_DEV f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ATX_DEV f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ATX_DEV f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// mask = (mask << 1) | sign(v): one SHF (ALU pipe) per test, no predicate, no branch
+ATX_DEV uint32_t shift_in_sign(uint32_t mask, float v)
+{
+    uint32_t r;
+    asm("shf.l.clamp.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(__float_as_uint(v)), "r"(mask));
+    return r;
+}
+
 // dot(a,b) as nvcc contracts glm's (x*x' + y*y') + z*z' for the reference:
 // mul(y,y') -> fma(x,x',.) -> fma(z,z',.)   (Renderer PTX, every dot product)
 ATX_DEV float fdot3(float ax, float ay, float az, float bx, float by, float bz)

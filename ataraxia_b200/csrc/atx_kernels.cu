@@ -22,6 +22,8 @@ namespace atxk
 // Scene pack. Runs the per-material subexpressions with the SAME device ops the
 // reference executes per bounce, so hoisting them here cannot change a bit.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float flip_sign(float v) { return __uint_as_float(__float_as_uint(v) ^ 0x80000000u); }
+
 __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSpheres,
                                   const float* __restrict__ matAoS, uint32_t nMaterials,
                                   const float* __restrict__ lightAoS, uint32_t nLights,
@@ -33,7 +35,8 @@ __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSp
     {
         const float* s = sphAoS + 5 * i; // Sphere: center[3], radius, id (20 B)
         const float r = s[3];
-        spheres[i] = make_float4(s[0], s[1], s[2], r);
+        // centre stored negated (pure sign flip): o - c == o + (-c) bit for bit
+        spheres[i] = make_float4(flip_sign(s[0]), flip_sign(s[1]), flip_sign(s[2]), r);
         int32_t id = reinterpret_cast<const int32_t*>(s)[4];
         if (static_cast<uint32_t>(id) >= nMaterials) // Renderer.cu:30-37
             id = 0;
@@ -71,15 +74,20 @@ __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSp
 }
 
 // ---------------------------------------------------------------------------
-// Shared-memory sphere staging.
+// Shared-memory sphere staging. The resident array is padded with zero records up to a
+// multiple of 8 so the packed loop can run whole groups; padded slots are masked out of
+// the candidate set, never tested.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t round_up8(uint32_t n) { return (n + 7u) & ~7u; }
+
 __device__ __forceinline__ void stage_spheres(float4* dst, const float4* __restrict__ src, uint32_t count)
 {
-    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
-        dst[i] = __ldg(src + i);
+    const uint32_t padded = round_up8(count);
+    for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x)
+        dst[i] = i < count ? __ldg(src + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// trace one ray against spheres [0, count) resident at `sph` (shared memory); indices offset by base
+// scalar: one ray against spheres [0, count) resident at `sph`; indices offset by base
 __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, uint32_t base,
                                             float ox, float oy, float oz, float dx, float dy, float dz,
                                             const RayConst& k, float& tmin, int& closest)
@@ -89,8 +97,53 @@ __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, u
         intersect_sphere(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
 }
 
-// pixel of this thread: a CTA of 256 threads covers a 32x8 tile, each warp an 8x4
-// sub-tile (coherent primary rays; 4 x 128 B contiguous float4 segments per warp).
+// packed: the two rays of a thread against spheres [0, count) resident at `sph` (padded to
+// a multiple of 8). Blocks of 32 spheres: branch-free line filter into two sign masks, then
+// the few candidates of each lane are resolved with the exact sequence, lowest index first
+// (Renderer::traceRay keeps the lowest index on ties: strict '<', Renderer.cu:272).
+__device__ __forceinline__ void trace_range2(const float4* sph, uint32_t count, uint32_t base, const RayPair& rp,
+                                             const PathState& s0, const PathState& s1, bool live0, bool live1,
+                                             const RayConst& k0, const RayConst& k1,
+                                             float& tmin0, int& closest0, float& tmin1, int& closest1)
+{
+    for (uint32_t b = 0; b < count; b += 32u)
+    {
+        const uint32_t cnt = min(32u, count - b);
+        const uint32_t groups = (cnt + 7u) >> 3;
+        uint32_t m0 = 0u, m1 = 0u;
+        const float4* q = sph + b;
+#pragma unroll 1
+        for (uint32_t g = 0; g < groups; g++, q += 8)
+        {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                filter_sphere(q[i], rp, m0, m1);
+        }
+        // sphere i of the block sits at bit (8*groups-1-i): left-align so it is bit (31-i)
+        const uint32_t sh = 32u - 8u * groups;
+        const uint32_t valid = 0xFFFFFFFFu << (32u - cnt);
+        uint32_t c0 = live0 ? ((~m0 << sh) & valid) : 0u;
+        uint32_t c1 = live1 ? ((~m1 << sh) & valid) : 0u;
+        while (c0 | c1)
+        {
+            if (c0)
+            {
+                const uint32_t i = __clz(c0);
+                c0 &= ~(0x80000000u >> i);
+                exact_test(sph[b + i], static_cast<int>(base + b + i), s0.ox, s0.oy, s0.oz, s0.dx, s0.dy, s0.dz, k0, tmin0, closest0);
+            }
+            if (c1)
+            {
+                const uint32_t i = __clz(c1);
+                c1 &= ~(0x80000000u >> i);
+                exact_test(sph[b + i], static_cast<int>(base + b + i), s1.ox, s1.oy, s1.oz, s1.dx, s1.dy, s1.dz, k1, tmin1, closest1);
+            }
+        }
+    }
+}
+
+// pixel of this thread, one pixel per thread: a CTA of 256 threads covers a 32x8 tile, each
+// warp an 8x4 sub-tile (coherent primary rays; 4 x 128 B contiguous float4 segments per warp).
 __device__ __forceinline__ void thread_pixel(uint32_t& x, uint32_t& y)
 {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -98,36 +151,75 @@ __device__ __forceinline__ void thread_pixel(uint32_t& x, uint32_t& y)
     y = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
 }
 
+// two horizontally adjacent pixels per thread (x, y) and (x+1, y): a CTA covers 64x8, a warp
+// 16x4; a thread's two float4 accumulators are 32 contiguous bytes.
+__device__ __forceinline__ void thread_pixel_pair(uint32_t& x, uint32_t& y)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    x = blockIdx.x * 64u + (warp & 3u) * 16u + (lane & 7u) * 2u;
+    y = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
+}
+
+__device__ __forceinline__ void count_rays(const RenderParams& p, uint32_t rays, uint32_t paths)
+{
+    // exact counters: one atomic per warp (all 32 lanes of the warp reach this point)
+    if (!p.counters)
+        return;
+    unsigned long long r = rays, n = paths;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31u) == 0)
+    {
+        atomicAdd(p.counters + 0, n);
+        atomicAdd(p.counters + 1, r);
+    }
+}
+
+// perPixel's loop does not run when maxBounces < 1: every sample is (0,0,0,1)   (Renderer.cu:303-304, :386)
+__device__ __forceinline__ void accumulate_black(float4& acc, uint32_t n)
+{
+    for (uint32_t q = 0; q < n; q++)
+    {
+        acc.x = fadd(0.0f, acc.x); acc.y = fadd(0.0f, acc.y); acc.z = fadd(0.0f, acc.z);
+        acc.w = fadd(acc.w, 1.0f);
+    }
+}
+
 // ---------------------------------------------------------------------------
-// The megakernel.
+// Megakernel, while-while form (small scenes: shading dominates the sphere loop).
 //
-// Per thread: pixel p, frames f = firstFrame + j*frameStride, j < nFrames. The path
-// loop of Renderer::perPixel is flattened: every iteration traces ONE ray (closest
-// hit or shadow) against all spheres and then runs the matching half of the bounce.
-// When a path ends the sample is added to the running sum and the next frame's path
-// starts in the same iteration (path regeneration), so lanes stay busy until their
-// last frame instead of idling at the slowest path of every frame.
-//
-// kChunked: the sphere array is larger than one shared-memory chunk; the CTA then
-// walks the chunks in lockstep (double-buffered), which needs the outer loop to be
-// CTA-uniform (__syncthreads_or on "any thread still has work").
+// One thread = one pixel, all requested frames f = firstFrame + j*frameStride of it. The
+// warp alternates between two phases:
+//   A  lanes without a pending hit trace their closest-hit ray; a miss ends the path,
+//      adds the sample to the running sum and starts the next frame's path at once (path
+//      regeneration); a hit is parked. Up to traceRounds rounds, or until every live lane
+//      has a hit parked.
+//   B  lanes with a parked hit run the whole bounce in lockstep: hit record, emission,
+//      light pick, shadow trace, Cook-Torrance, Russian roulette, next direction.
+// Phase B is the expensive part (~5x a 3-sphere trace); gathering hits before entering it
+// keeps its lanes full, and lanes that drift apart (a bounce ray that hits something)
+// fall back into step on the next round instead of staying out of phase for the rest of
+// the launch. The samples of a pixel are summed in registers in frame order, so the
+// float4 sums are bit-identical to sequential reference frames, and the accumulation
+// buffer is touched once: one 16 B read + one 16 B write per pixel per launch.
 // ---------------------------------------------------------------------------
-template <bool kChunked>
-__global__ void __launch_bounds__(256, 2) megakernel(const RenderParams p)
+__global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 {
     extern __shared__ float4 smem[];
     float4* sphS = smem;
+    constexpr unsigned kFull = 0xffffffffu;
 
     uint32_t x, y;
     thread_pixel(x, y);
     const bool inside = x < p.width && y < p.height;
     const uint32_t pixel = x + y * p.width;
 
-    if (!kChunked)
-    {
-        stage_spheres(sphS, p.spheres, p.nSpheres);
-        __syncthreads();
-    }
+    stage_spheres(sphS, p.spheres, p.nSpheres);
+    __syncthreads();
 
     // running sum starts from the stored value so the additions happen in the same
     // order as the reference's per-frame "accumulation[p] += color" (Renderer.cu:165)
@@ -139,217 +231,267 @@ __global__ void __launch_bounds__(256, 2) megakernel(const RenderParams p)
     if (inside)
         d0 = primary_direction(p.cam, x, y, p.width, p.height);
 
-    // path state
-    uint32_t j = 0;                       // frames done
+    uint32_t j = 0; // frames done
     uint32_t frame = p.firstFrame;
     bool alive = inside && p.nFrames > 0;
     if (alive && p.maxBounces < 1)
     {
-        // perPixel's loop does not run: every sample is (0,0,0,1)   (Renderer.cu:303-304, :386)
-        for (uint32_t q = 0; q < p.nFrames; q++)
-        {
-            acc.x = fadd(0.0f, acc.x); acc.y = fadd(0.0f, acc.y); acc.z = fadd(0.0f, acc.z);
-            acc.w = fadd(acc.w, 1.0f);
-        }
+        accumulate_black(acc, p.nFrames);
         j = p.nFrames;
         alive = false;
     }
 
-    float ox = p.cam.pos[0], oy = p.cam.pos[1], oz = p.cam.pos[2];
-    float dx = d0.x, dy = d0.y, dz = d0.z;
-    float cr = 0.0f, cg = 0.0f, cb = 0.0f;     // color
-    float tx = 1.0f, ty = 1.0f, tz = 1.0f;     // throughput
-    uint32_t seed = pixel * frame;             // Renderer.cu:300-301 (bounce 0 adds 0)
-    int bounce = 0;
-    int phase = 0;                             // 0 = closest-hit ray in flight, 1 = shadow ray in flight
-    // carried from the closest-hit half to the shadow half of a bounce
-    V3 N = { 0.0f, 0.0f, 0.0f }, V = { 0.0f, 0.0f, 0.0f };
-    float dist2 = 0.0f;
-    int matIndex = 0;
-    uint32_t lightIndex = 0;
+    PathState s;
+    path_begin(s, p.cam.pos, d0, pixel, frame);
+    bool pending = false;
+    float tminP = 0.0f;
+    int closestP = -1;
     uint32_t rays = 0;
 
-    while (kChunked ? __syncthreads_or(alive) : alive)
+    // the sample is complete: add it and start the next frame's path, or retire the lane
+    auto finish = [&]() {
+        accumulate_sample(acc, s);
+        j++;
+        if (j >= p.nFrames)
+            alive = false;
+        else
+        {
+            frame += p.frameStride;
+            path_begin(s, p.cam.pos, d0, pixel, frame);
+        }
+    };
+
+    while (__any_sync(kFull, alive))
     {
-        // ---- trace the ray in flight against every sphere (Renderer::traceRay) ----
-        float tmin = 3.402823466e+38f; // FLT_MAX
-        int closest = -1;
-        const RayConst rk = ray_constants(dx, dy, dz);
-        if (!kChunked)
+        // ---- phase A: closest-hit rounds ----
+#pragma unroll 1
+        for (uint32_t round = 0; round < p.traceRounds; round++)
         {
-            trace_range(sphS, p.nSpheres, 0u, ox, oy, oz, dx, dy, dz, rk, tmin, closest);
-        }
-        else
-        {
-            // double-buffered chunk walk; all threads of the CTA take part in staging
-            const uint32_t C = p.chunkSpheres;
-            const uint32_t nChunks = (p.nSpheres + C - 1) / C;
-            stage_spheres(sphS, p.spheres, min(C, p.nSpheres));
-            for (uint32_t c = 0; c < nChunks; c++)
+            const bool act = alive && !pending;
+            if (!__any_sync(kFull, act))
+                break;
+            if (act)
             {
-                __syncthreads(); // chunk c is resident
-                float4* cur = sphS + (c & 1u) * C;
-                if (c + 1 < nChunks)
-                    stage_spheres(sphS + ((c + 1) & 1u) * C, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C));
-                if (alive)
-                    trace_range(cur, min(C, p.nSpheres - c * C), c * C, ox, oy, oz, dx, dy, dz, rk, tmin, closest);
-            }
-            __syncthreads(); // nobody still reads the buffers when the next iteration restages
-            if (!alive)
-                continue;
-        }
-        rays++;
-
-        bool pathEnds = false;
-        bool doBounce = false;
-        if (phase == 0)
-        {
-            if (closest < 0)
-            {
-                // miss (Renderer.cu:309-318)
-                if (p.skyLight)
+                float tmin = 3.402823466e+38f; // FLT_MAX
+                int closest = -1;
+                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+                rays++;
+                if (closest < 0)
                 {
-                    cr = ffma(tx, 0.6f, cr);
-                    cg = ffma(ty, 0.7f, cg);
-                    cb = ffma(tz, 0.9f, cb);
-                }
-                pathEnds = true;
-            }
-            else
-            {
-                const float4 sp = kChunked ? __ldg(p.spheres + closest) : sphS[closest];
-                V3 wp;
-                hit_record(sp, ox, oy, oz, dx, dy, dz, tmin, wp, N);
-                matIndex = __ldg(p.sphMat + closest);
-                const float4 m4 = __ldg(p.mats + kMatStride * matIndex + 4);
-                if (m4.w > 0.0f) // emission (Renderer.cu:329-333)
-                {
-                    cr = ffma(tx, m4.x, cr);
-                    cg = ffma(ty, m4.y, cg);
-                    cb = ffma(tz, m4.z, cb);
-                }
-                // next origin == shadow origin: pos + N*1e-4 (Renderer.cu:348, :372), an fma
-                const float nox = ffma(N.x, 0.0001f, wp.x);
-                const float noy = ffma(N.y, 0.0001f, wp.y);
-                const float noz = ffma(N.z, 0.0001f, wp.z);
-                if (p.nLights > 0)
-                {
-                    // light pick reuses the un-advanced seed (Renderer.cu:340)
-                    lightIndex = pcg_hash(seed) % p.nLights;
-                    const float4 lp = __ldg(p.lights + kLightStride * lightIndex);
-                    const float lx = fsub(lp.x, wp.x), ly = fsub(lp.y, wp.y), lz = fsub(lp.z, wp.z);
-                    dist2 = fdot3(lx, ly, lz, lx, ly, lz);
-                    const float inv = frsqrt_approx(dist2);
-                    V = { fsub(0.0f, dx), fsub(0.0f, dy), fsub(0.0f, dz) }; // V = -ray.direction (Renderer.cu:359)
-                    dx = fmul(lx, inv); dy = fmul(inv, ly); dz = fmul(inv, lz);
-                    phase = 1;
+                    path_miss(p, s);
+                    finish();
                 }
                 else
                 {
-                    doBounce = true;
+                    pending = true;
+                    tminP = tmin;
+                    closestP = closest;
                 }
-                ox = nox; oy = noy; oz = noz;
             }
         }
-        else
+        // ---- phase B: one bounce for every parked hit ----
+        if (pending)
         {
-            // shadow result (Renderer.cu:351-368): occluded iff t > 0 && t*t < dist2
-            const float ts = closest < 0 ? -1.0f : tmin;
-            if (!(ts > 0.0f && fmul(ts, ts) < dist2))
+            pending = false;
+            bool ends = false;
+            if (path_hit(p, s, sphS[closestP], closestP, tminP))
             {
-                const float4 m0 = __ldg(p.mats + kMatStride * matIndex + 0);
-                const float4 m1 = __ldg(p.mats + kMatStride * matIndex + 1);
-                const float4 m2 = __ldg(p.mats + kMatStride * matIndex + 2);
-                const float4 m3 = __ldg(p.mats + kMatStride * matIndex + 3);
-                const V3 L = { dx, dy, dz };
-                const V3 s = cook_torrance(m0, m1, m2, m3, N, V, L);
-                const float4 le = __ldg(p.lights + kLightStride * lightIndex + 1);
-                // color += emission * specular * throughput / pdf(=1)   (Renderer.cu:362-367): ptxas folds
-                // the division by 1 and contracts the last product into the sum (kernelRender SASS 0x32d0-0x3350)
-                cr = ffma(fmul(le.x, s.x), tx, cr);
-                cg = ffma(fmul(le.y, s.y), ty, cg);
-                cb = ffma(fmul(le.z, s.z), tz, cb);
+                float tmin = 3.402823466e+38f;
+                int closest = -1;
+                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+                rays++;
+                path_shadow(p, s, closest, tmin);
             }
-            doBounce = true;
-        }
-
-        if (doBounce)
-        {
-            // throughput, Russian roulette, next direction (Renderer.cu:371-384)
-            const float4 m0 = __ldg(p.mats + kMatStride * matIndex + 0);
-            const float4 m1 = __ldg(p.mats + kMatStride * matIndex + 1);
-            tx = fmul(tx, m0.x); ty = fmul(ty, m0.y); tz = fmul(tz, m0.z);
-            const float len = fsqrt_approx(fdot3(tx, ty, tz, tx, ty, tz));
-            const float pr = fmax_(fmin_(len, 1.0f), 0.1f);
-            if (pcg_float(seed) > pr)
-            {
-                pathEnds = true;
-            }
-            else
-            {
-                tx = fdiv_approx(tx, pr); ty = fdiv_approx(ty, pr); tz = fdiv_approx(tz, pr);
-                V3 nd;
-                if (m1.w > 0.0f)
-                    nd = sample_ggx(N, __ldg(p.mats + kMatStride * matIndex + 5).x, seed);
-                else
-                    nd = sample_cosine(N, seed);
-                dx = nd.x; dy = nd.y; dz = nd.z;
-                phase = 0;
-                bounce++;
-                if (bounce >= p.maxBounces)
-                    pathEnds = true;
-                else
-                    seed += static_cast<uint32_t>(bounce); // Renderer.cu:306
-            }
-        }
-
-        if (pathEnds)
-        {
-            // accumulation[p] += vec4(color, 1)   (Renderer.cu:165, :386)
-            acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
-            acc.w = fadd(acc.w, 1.0f);
-            j++;
-            if (j >= p.nFrames)
-            {
-                alive = false;
-            }
-            else
-            {
-                frame += p.frameStride;
-                ox = p.cam.pos[0]; oy = p.cam.pos[1]; oz = p.cam.pos[2];
-                dx = d0.x; dy = d0.y; dz = d0.z;
-                cr = cg = cb = 0.0f;
-                tx = ty = tz = 1.0f;
-                seed = pixel * frame;
-                bounce = 0;
-                phase = 0;
-            }
+            ends = path_bounce(p, s);
+            if (ends)
+                finish();
         }
     }
 
     if (inside)
     {
-        p.accum[pixel] = acc; // st.global.v4.f32, 512 B contiguous per warp row group
+        p.accum[pixel] = acc; // st.global.v4.f32, 4 x 128 B contiguous per warp
         if (p.emitRgba)
             p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
     }
+    count_rays(p, rays, j);
+}
 
-    // exact counters: one atomic per warp
-    if (p.counters)
+// ---------------------------------------------------------------------------
+// Megakernel, two-slot packed form (large scenes: the sphere loop dominates).
+//
+// One thread = two adjacent pixels = two path slots. The path loop of
+// Renderer::perPixel is flattened: every iteration traces ONE ray per slot (closest hit
+// or shadow, whichever that slot's path needs next) against all spheres with the packed
+// f32x2 loop (trace_range2), then runs the matching half of the bounce per slot. A slot
+// whose path ends adds its sample and starts the next frame's path in the same
+// iteration, so both lanes of every packed instruction carry a live ray until the slot's
+// last frame.
+//
+// kChunked: the sphere array does not fit the shared-memory budget; the CTA walks it in
+// double-buffered chunks in lockstep, which needs the outer loop to be CTA-uniform
+// (__syncthreads_or on "any thread still has work").
+// ---------------------------------------------------------------------------
+struct Slot
+{
+    PathState s;
+    float4 acc;
+    V3 d0;
+    uint32_t pixel;
+    uint32_t j;      // frames done
+    uint32_t frame;
+    bool alive;
+    bool shadow;     // the ray in flight is a shadow ray
+};
+
+__device__ __forceinline__ void slot_init(const RenderParams& p, Slot& t, uint32_t x, uint32_t y)
+{
+    const bool inside = x < p.width && y < p.height;
+    t.pixel = x + y * p.width;
+    t.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    t.d0 = { 0.0f, 0.0f, 0.0f };
+    if (inside)
     {
-        unsigned long long r = rays, paths = j; // j == 0 for threads outside the image
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        if (!p.zeroFirst)
+            t.acc = p.accum[t.pixel];
+        t.d0 = primary_direction(p.cam, x, y, p.width, p.height);
+    }
+    t.j = 0;
+    t.frame = p.firstFrame;
+    t.alive = inside && p.nFrames > 0;
+    t.shadow = false;
+    if (t.alive && p.maxBounces < 1)
+    {
+        accumulate_black(t.acc, p.nFrames);
+        t.j = p.nFrames;
+        t.alive = false;
+    }
+    path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
+}
+
+__device__ __forceinline__ void slot_finish(const RenderParams& p, Slot& t)
+{
+    accumulate_sample(t.acc, t.s);
+    t.j++;
+    t.shadow = false;
+    if (t.j >= p.nFrames)
+        t.alive = false;
+    else
+    {
+        t.frame += p.frameStride;
+        path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
+    }
+}
+
+// the half-bounce that follows the trace of this slot's ray
+template <bool kChunked>
+__device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, const float4* sphS, int closest, float tmin)
+{
+    bool bounce = false;
+    if (!t.shadow)
+    {
+        if (closest < 0)
         {
-            r += __shfl_xor_sync(0xffffffffu, r, o);
-            paths += __shfl_xor_sync(0xffffffffu, paths, o);
+            path_miss(p, t.s);
+            slot_finish(p, t);
+            return;
         }
-        if ((threadIdx.x & 31u) == 0)
+        const float4 sp = kChunked ? __ldg(p.spheres + closest) : sphS[closest];
+        if (path_hit(p, t.s, sp, closest, tmin))
+            t.shadow = true;
+        else
+            bounce = true;
+    }
+    else
+    {
+        path_shadow(p, t.s, closest, tmin);
+        t.shadow = false;
+        bounce = true;
+    }
+    if (bounce && path_bounce(p, t.s))
+        slot_finish(p, t);
+}
+
+template <bool kChunked>
+__global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
+{
+    extern __shared__ float4 smem[];
+    float4* sphS = smem;
+
+    uint32_t x, y;
+    thread_pixel_pair(x, y);
+
+    if (!kChunked)
+    {
+        stage_spheres(sphS, p.spheres, p.nSpheres);
+        __syncthreads();
+    }
+
+    Slot a, b;
+    slot_init(p, a, x, y);
+    slot_init(p, b, x + 1u, y);
+    uint32_t rays = 0;
+
+    while (kChunked ? __syncthreads_or(a.alive || b.alive) : (a.alive || b.alive))
+    {
+        // ---- trace the ray in flight of each slot against every sphere (Renderer::traceRay) ----
+        float tmin0 = 3.402823466e+38f, tmin1 = 3.402823466e+38f; // FLT_MAX
+        int closest0 = -1, closest1 = -1;
+        const RayConst k0 = ray_constants(a.s.dx, a.s.dy, a.s.dz);
+        const RayConst k1 = ray_constants(b.s.dx, b.s.dy, b.s.dz);
+        RayPair rp;
+        rp.ox = pk2(a.s.ox, b.s.ox); rp.oy = pk2(a.s.oy, b.s.oy); rp.oz = pk2(a.s.oz, b.s.oz);
+        rp.dx = pk2(a.s.dx, b.s.dx); rp.dy = pk2(a.s.dy, b.s.dy); rp.dz = pk2(a.s.dz, b.s.dz);
+        rp.na = pk2(fneg(k0.a), fneg(k1.a));
+        if (!kChunked)
         {
-            atomicAdd(p.counters + 0, paths);
-            atomicAdd(p.counters + 1, r);
+            trace_range2(sphS, p.nSpheres, 0u, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
+        }
+        else
+        {
+            // double-buffered chunk walk; all threads of the CTA take part in staging
+            const uint32_t C = p.chunkSpheres, stride = round_up8(C);
+            const uint32_t nChunks = (p.nSpheres + C - 1) / C;
+            stage_spheres(sphS, p.spheres, min(C, p.nSpheres));
+            for (uint32_t c = 0; c < nChunks; c++)
+            {
+                __syncthreads(); // chunk c is resident
+                const float4* cur = sphS + (c & 1u) * stride;
+                if (c + 1 < nChunks)
+                    stage_spheres(sphS + ((c + 1) & 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C));
+                if (a.alive || b.alive)
+                    trace_range2(cur, min(C, p.nSpheres - c * C), c * C, rp, a.s, b.s, a.alive, b.alive, k0, k1,
+                                 tmin0, closest0, tmin1, closest1);
+            }
+            __syncthreads(); // nobody still reads the buffers when the next iteration restages
+        }
+        if (a.alive)
+        {
+            rays++;
+            slot_advance<kChunked>(p, a, sphS, closest0, tmin0);
+        }
+        if (b.alive)
+        {
+            rays++;
+            slot_advance<kChunked>(p, b, sphS, closest1, tmin1);
         }
     }
+
+    if (x < p.width && y < p.height)
+    {
+        p.accum[a.pixel] = a.acc;
+        if (p.emitRgba)
+            p.rgba[a.pixel] = pack_rgba8(a.acc, u32_to_f32_rn(p.rgbaDivisor));
+        if (x + 1u < p.width)
+        {
+            p.accum[b.pixel] = b.acc;
+            if (p.emitRgba)
+                p.rgba[b.pixel] = pack_rgba8(b.acc, u32_to_f32_rn(p.rgbaDivisor));
+        }
+    }
+    count_rays(p, rays, a.j + b.j);
 }
 
 // ---------------------------------------------------------------------------
@@ -411,29 +553,49 @@ cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, ui
     return cudaGetLastError();
 }
 
+// which megakernel form a launch uses: the while-while form needs the whole scene resident
+int mega_kind(const RenderParams& p, int requested)
+{
+    const bool chunked = p.chunkSpheres < p.nSpheres;
+    if (chunked)
+        return kMegaPair;
+    if (requested == kMegaWhileWhile || requested == kMegaPair)
+        return requested;
+    return p.nSpheres <= kWhileWhileMaxSpheres ? kMegaWhileWhile : kMegaPair;
+}
+
 size_t megakernel_smem_bytes(const RenderParams& p)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
-    return sizeof(float4) * (chunked ? 2ull * p.chunkSpheres : static_cast<size_t>(p.nSpheres));
+    const size_t pad8 = (static_cast<size_t>(chunked ? p.chunkSpheres : p.nSpheres) + 7u) & ~size_t(7);
+    return sizeof(float4) * (chunked ? 2 * pad8 : pad8);
 }
 
 cudaError_t configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(megakernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(megakernel_ww, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(megakernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    e = cudaFuncSetAttribute(megakernel_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
 }
 
-cudaError_t render_mega(const RenderParams& p, cudaStream_t s)
+cudaError_t render_mega(const RenderParams& p, int kind, cudaStream_t s)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
     const size_t smem = megakernel_smem_bytes(p);
-    const dim3 grid = tile_grid(p.width, p.height);
-    if (chunked)
-        megakernel<true><<<grid, 256, smem, s>>>(p);
+    if (mega_kind(p, kind) == kMegaWhileWhile)
+        megakernel_ww<<<tile_grid(p.width, p.height), 256, smem, s>>>(p);
     else
-        megakernel<false><<<grid, 256, smem, s>>>(p);
+    {
+        const dim3 grid((p.width + 63u) / 64u, (p.height + 7u) / 8u);
+        if (chunked)
+            megakernel_pair<true><<<grid, 256, smem, s>>>(p);
+        else
+            megakernel_pair<false><<<grid, 256, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per step (default: the workload's)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference-CUDA legs")
+    ap.add_argument("--mega-kind", type=int, default=0, help="0 auto, 1 while-while, 2 two-slot packed (same results)")
+    ap.add_argument("--trace-rounds", type=int, default=0, help="while-while form: closest-hit rounds per shading phase")
+    ap.add_argument("--chunk", type=int, default=0, help="force the shared-memory chunk size in spheres (0 = automatic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -214,6 +217,11 @@ def main():
     cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
     r = atx.Renderer(local_rank)
     r.setSettings(atx.Settings(True, False, bounces))
+    r.setTuning(atx.TUNE_MEGA_KIND, args.mega_kind)
+    if args.trace_rounds:
+        r.setTuning(atx.TUNE_TRACE_ROUNDS, args.trace_rounds)
+    if args.chunk:
+        r.setTuning(atx.TUNE_CHUNK_SPHERES, args.chunk)
     r.onResize(W, H)
     cam.Resize(W, H)
     spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
@@ -315,7 +323,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
                        "spheres": int(len(spheres)), "lights": int(len(lights)), "parallelism": f"spp-split x{world}",
-                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel"},
+                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel", "mega_kind": args.mega_kind, "trace_rounds": args.trace_rounds, "chunk": args.chunk},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "wall_ms_total": wall_ms,
             "gpu_launches": launches,

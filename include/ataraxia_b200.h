@@ -136,8 +136,12 @@ ATX_API atx_status atx_set_settings(atx_handle h, int accumulation, int sky_ligh
 
 /* Tuning knobs that never change results (parity tests sweep them). */
 enum {
-    ATX_TUNE_CHUNK_SPHERES = 1 /* spheres per shared-memory chunk; 0 = automatic. Forces the
-                                  chunked (double-buffered) staging path when < n_spheres. */
+    ATX_TUNE_CHUNK_SPHERES = 1, /* spheres per shared-memory chunk; 0 = automatic. Forces the
+                                   chunked (double-buffered) staging path when < n_spheres. */
+    ATX_TUNE_MEGA_KIND = 2,     /* megakernel form: 0 = by sphere count, 1 = while-while (one pixel
+                                   per thread, hits gathered before the shading phase), 2 = two-slot
+                                   packed (two pixels per thread, f32x2 sphere loop) */
+    ATX_TUNE_TRACE_ROUNDS = 3   /* while-while form: closest-hit rounds per shading phase (default 2) */
 };
 ATX_API atx_status atx_set_tuning(atx_handle h, int key, int64_t value);
 

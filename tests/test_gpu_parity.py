@@ -194,12 +194,37 @@ def test_chunked_staging_is_bit_identical(atx):
     r, cam = setup(atx, scene, 192, 108, 6, True)
     r.Render(cam, scene, frames=3)
     base = r.getAccumulation()
-    for chunk in (1, 7, 16, 39, 40):
+    for chunk in (1, 7, 8, 16, 32, 39, 40):
         r.setTuning(atx.TUNE_CHUNK_SPHERES, chunk)
         r.resetFrameIndex()
         r.Render(cam, scene, frames=3)
         assert (bits(r.getAccumulation()) == bits(base)).all(), chunk
     r.close()
+
+
+def test_megakernel_forms_are_bit_identical(atx):
+    """while-while (1 pixel/thread) and two-slot packed (f32x2 sphere loop) forms, any trace-round count,
+    odd image sizes (partial tiles, an unpaired last column), sphere counts around the 8/32 block edges."""
+    cases = [(atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 161, 91, 8, False, 5),
+             (atx.synthetic.small(40, 3, seed=21), 192, 108, 6, True, 3),
+             (atx.synthetic.small(33, 2, seed=5), 97, 55, 8, True, 4),
+             (atx.synthetic.small(8, 1, seed=6), 64, 40, 8, False, 4),
+             (atx.synthetic.small(70, 0, seed=7), 80, 48, 5, True, 3)]
+    for scene, W, H, bounces, sky, frames in cases:
+        r, cam = setup(atx, scene, W, H, bounces, sky)
+        ref = None
+        for kind, rounds in ((atx.MEGA_WHILE_WHILE, 1), (atx.MEGA_WHILE_WHILE, 2), (atx.MEGA_WHILE_WHILE, 5), (atx.MEGA_PAIR, 2)):
+            r.setTuning(atx.TUNE_MEGA_KIND, kind)
+            r.setTuning(atx.TUNE_TRACE_ROUNDS, rounds)
+            r.resetFrameIndex(); r.resetCounters()
+            r.Render(cam, scene, frames=frames)
+            acc, c = r.getAccumulation(), r.counters()
+            assert (acc[..., 3] == frames).all() and c.paths == W * H * frames
+            if ref is None:
+                ref = (acc, c.rays)
+            assert (bits(acc) == bits(ref[0])).all(), (kind, rounds, W, H)
+            assert c.rays == ref[1]
+        r.close()
 
 
 def test_split_launches_and_determinism(atx):
