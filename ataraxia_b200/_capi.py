@@ -39,7 +39,8 @@ assert SPHERE_DTYPE.itemsize == 20 and MATERIAL_DTYPE.itemsize == 52 and LIGHT_D
 
 
 class Counters(C.Structure):
-    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("launches", C.c_uint64)]
+    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("sphere_tests", C.c_uint64), ("launches", C.c_uint64),
+                ("rays_traced", C.c_uint64), ("sphere_tests_executed", C.c_uint64)]
 
 
 class AtxError(RuntimeError):

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     # device: the reference is built -use_fast_math; its three effects are requested one by
     # one so that nothing else (e.g. host-side fast math) comes along. All float arithmetic
     # in the kernels is explicit PTX (atx_exact.cuh), -ftz only decides the setp flavour.
-    "-ftz=true", "-prec-div=false", "-prec-sqrt=false",
+    "-ftz=true", "-prec-div=false", "-prec-sqrt=false", *os.environ.get("ATX_EXTRA_NVCC", "").split(),
     # host: glm-order math must not be contracted or reassociated
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden",
 ]

@@ -637,6 +637,8 @@ atx_status atx_get_counters(atx_handle h, atx_counters* out)
     out->rays = c[1];
     out->sphere_tests = c[1] * h->nS; // every traceRay tests every sphere (Renderer.cu:256)
     out->launches = h->launches;
+    out->rays_traced = c[2];
+    out->sphere_tests_executed = c[2] * h->nS;
     return ATX_OK;
 }
 

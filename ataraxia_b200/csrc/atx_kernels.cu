@@ -97,46 +97,97 @@ __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, u
         intersect_sphere(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
 }
 
-// packed: the two rays of a thread against spheres [0, count) resident at `sph` (padded to
-// a multiple of 8). Blocks of 32 spheres: branch-free line filter into two sign masks, then
-// the few candidates of each lane are resolved with the exact sequence, lowest index first
-// (Renderer::traceRay keeps the lowest index on ties: strict '<', Renderer.cu:272).
-__device__ __forceinline__ void trace_range2(const float4* sph, uint32_t count, uint32_t base, const RayPair& rp,
-                                             const PathState& s0, const PathState& s1, bool live0, bool live1,
-                                             const RayConst& k0, const RayConst& k1,
+// packed: the two rays of a thread against spheres [0, count) resident at `sph` (padded to a
+// multiple of 8). Two stages per super-block of up to kSuperBlock spheres:
+//   filter   blocks of 32 spheres, branch-free: two 32-bit candidate words per block go to this
+//            thread's private column of `cand` (shared memory, conflict-free), plus one bit per
+//            block in a "non-empty" word per slot;
+//   resolve  each lane walks its own candidates in ascending sphere index with the exact
+//            sequence (Renderer::traceRay keeps the lowest index on ties: strict '<',
+//            Renderer.cu:272). The loop runs max-over-lanes(candidates) times per super-block,
+//            not once per block, so the few lanes with work share their iterations.
+constexpr uint32_t kSuperBlock = 512;                   // spheres resolved together
+// candidate words per thread: two slots x blocks of the largest super-block a launch sees
+__host__ __device__ __forceinline__ uint32_t cand_words(const RenderParams& p)
+{
+    const uint32_t resident = p.chunkSpheres < p.nSpheres ? p.chunkSpheres : p.nSpheres;
+    const uint32_t span = resident < kSuperBlock ? resident : kSuperBlock;
+    return 2u * ((span + 31u) / 32u);
+}
+
+__device__ __forceinline__ void trace_range2(const float4* sph, uint32_t count, uint32_t base, uint32_t* cand,
+                                             const RayPair& rp, const PathState& s0, const PathState& s1,
+                                             bool live0, bool live1, const RayConst& k0, const RayConst& k1,
                                              float& tmin0, int& closest0, float& tmin1, int& closest1)
 {
-    for (uint32_t b = 0; b < count; b += 32u)
+    uint32_t* mine = cand + threadIdx.x; // word w of this thread: mine[w * blockDim.x]
+    for (uint32_t sb = 0; sb < count; sb += kSuperBlock)
     {
-        const uint32_t cnt = min(32u, count - b);
-        const uint32_t groups = (cnt + 7u) >> 3;
-        uint32_t m0 = 0u, m1 = 0u;
-        const float4* q = sph + b;
+        const uint32_t sbCount = min(kSuperBlock, count - sb);
+        const uint32_t nBlocks = (sbCount + 31u) >> 5;
+        uint32_t nz0 = 0u, nz1 = 0u;
+        const float4* q = sph + sb;
 #pragma unroll 1
-        for (uint32_t g = 0; g < groups; g++, q += 8)
+        for (uint32_t blk = 0; blk < nBlocks; blk++)
         {
+            const uint32_t cnt = min(32u, sbCount - blk * 32u);
+            const uint32_t groups = (cnt + 7u) >> 3;
+            uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll 1
+            for (uint32_t g = 0; g < groups; g++, q += 8)
+            {
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                filter_sphere(q[i], rp, m0, m1);
-        }
-        // sphere i of the block sits at bit (8*groups-1-i): left-align so it is bit (31-i)
-        const uint32_t sh = 32u - 8u * groups;
-        const uint32_t valid = 0xFFFFFFFFu << (32u - cnt);
-        uint32_t c0 = live0 ? ((~m0 << sh) & valid) : 0u;
-        uint32_t c1 = live1 ? ((~m1 << sh) & valid) : 0u;
-        while (c0 | c1)
-        {
-            if (c0)
-            {
-                const uint32_t i = __clz(c0);
-                c0 &= ~(0x80000000u >> i);
-                exact_test(sph[b + i], static_cast<int>(base + b + i), s0.ox, s0.oy, s0.oz, s0.dx, s0.dy, s0.dz, k0, tmin0, closest0);
+                for (int i = 0; i < 8; i++)
+                    filter_sphere(q[i], rp, m0, m1);
             }
-            if (c1)
+            uint32_t c0 = ~m0, c1 = ~m1;
+            if (cnt < 32u)
             {
-                const uint32_t i = __clz(c1);
-                c1 &= ~(0x80000000u >> i);
-                exact_test(sph[b + i], static_cast<int>(base + b + i), s1.ox, s1.oy, s1.oz, s1.dx, s1.dy, s1.dz, k1, tmin1, closest1);
+                // sphere i of the block sits at bit (8*groups-1-i): left-align so it is bit (31-i),
+                // and drop the zero-padded tail
+                const uint32_t sh = 32u - 8u * groups;
+                const uint32_t valid = 0xFFFFFFFFu << (32u - cnt);
+                c0 = (c0 << sh) & valid;
+                c1 = (c1 << sh) & valid;
+            }
+            mine[(2u * blk) * blockDim.x] = c0;
+            mine[(2u * blk + 1u) * blockDim.x] = c1;
+            nz0 = (nz0 << 1) | (c0 != 0u ? 1u : 0u);
+            nz1 = (nz1 << 1) | (c1 != 0u ? 1u : 0u);
+        }
+        // block blk at bit (31 - blk); a retired slot has no candidates
+        nz0 = live0 ? nz0 << (32u - nBlocks) : 0u;
+        nz1 = live1 ? nz1 << (32u - nBlocks) : 0u;
+        uint32_t cur0 = 0u, cur1 = 0u, b0 = 0u, b1 = 0u;
+        while (true)
+        {
+            if (cur0 == 0u && nz0 != 0u)
+            {
+                b0 = __clz(nz0);
+                nz0 &= ~(0x80000000u >> b0);
+                cur0 = mine[(2u * b0) * blockDim.x];
+            }
+            if (cur1 == 0u && nz1 != 0u)
+            {
+                b1 = __clz(nz1);
+                nz1 &= ~(0x80000000u >> b1);
+                cur1 = mine[(2u * b1 + 1u) * blockDim.x];
+            }
+            if ((cur0 | cur1) == 0u)
+                break;
+            if (cur0)
+            {
+                const uint32_t i = __clz(cur0);
+                cur0 &= ~(0x80000000u >> i);
+                const uint32_t idx = sb + b0 * 32u + i;
+                exact_test(sph[idx], static_cast<int>(base + idx), s0.ox, s0.oy, s0.oz, s0.dx, s0.dy, s0.dz, k0, tmin0, closest0);
+            }
+            if (cur1)
+            {
+                const uint32_t i = __clz(cur1);
+                cur1 &= ~(0x80000000u >> i);
+                const uint32_t idx = sb + b1 * 32u + i;
+                exact_test(sph[idx], static_cast<int>(base + idx), s1.ox, s1.oy, s1.oz, s1.dx, s1.dy, s1.dz, k1, tmin1, closest1);
             }
         }
     }
@@ -160,22 +211,24 @@ __device__ __forceinline__ void thread_pixel_pair(uint32_t& x, uint32_t& y)
     y = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
 }
 
-__device__ __forceinline__ void count_rays(const RenderParams& p, uint32_t rays, uint32_t paths)
+__device__ __forceinline__ void count_rays(const RenderParams& p, uint32_t rays, uint32_t traced, uint32_t paths)
 {
     // exact counters: one atomic per warp (all 32 lanes of the warp reach this point)
     if (!p.counters)
         return;
-    unsigned long long r = rays, n = paths;
+    unsigned long long r = rays, t = traced, n = paths;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
         r += __shfl_xor_sync(0xffffffffu, r, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
         n += __shfl_xor_sync(0xffffffffu, n, o);
     }
     if ((threadIdx.x & 31u) == 0)
     {
         atomicAdd(p.counters + 0, n);
         atomicAdd(p.counters + 1, r);
+        atomicAdd(p.counters + 2, t);
     }
 }
 
@@ -189,17 +242,39 @@ __device__ __forceinline__ void accumulate_black(float4& acc, uint32_t n)
     }
 }
 
+// A pixel whose primary ray misses every sphere: each frame's path is "miss at bounce 0"
+// (Renderer.cu:309-318 with throughput 1), so all its samples are added in one short loop.
+__device__ __forceinline__ void accumulate_sky(const RenderParams& p, float4& acc, uint32_t n)
+{
+    PathState s;
+    s.cr = s.cg = s.cb = 0.0f;
+    s.tx = s.ty = s.tz = 1.0f;
+    path_miss(p, s);
+    for (uint32_t q = 0; q < n; q++)
+        accumulate_sample(acc, s);
+}
+
+// ---------------------------------------------------------------------------
+// The primary ray of a pixel is the same every frame: Camera::UpdateRayDirection has no
+// jitter and no half-pixel offset (Camera.cpp:176-187), and ray.origin is the camera
+// position (Renderer.cu:291-293). Its traceRay result (t, sphere) is therefore a per-pixel
+// constant of the launch: both megakernel forms trace it once in their prologue and start
+// every frame's path from that hit record. The first traceRay call of frames 2..n is not
+// executed; `rays` still counts it (it is a traceRay call of the reference), `traced`
+// counts the rays whose sphere loop really ran (the roofline uses `traced`).
+// ---------------------------------------------------------------------------
+
 // ---------------------------------------------------------------------------
 // Megakernel, while-while form (small scenes: shading dominates the sphere loop).
 //
 // One thread = one pixel, all requested frames f = firstFrame + j*frameStride of it. The
 // warp alternates between two phases:
-//   A  lanes without a pending hit trace their closest-hit ray; a miss ends the path,
-//      adds the sample to the running sum and starts the next frame's path at once (path
-//      regeneration); a hit is parked. Up to traceRounds rounds, or until every live lane
-//      has a hit parked.
 //   B  lanes with a parked hit run the whole bounce in lockstep: hit record, emission,
-//      light pick, shadow trace, Cook-Torrance, Russian roulette, next direction.
+//      light pick, shadow trace, Cook-Torrance, Russian roulette, next direction;
+//   A  lanes with a bounce ray in flight trace it; a miss ends the path, adds the sample
+//      to the running sum and starts the next frame's path at once (path regeneration) -
+//      which parks the cached primary hit; a hit is parked. Up to traceRounds rounds, or
+//      until every live lane has a hit parked.
 // Phase B is the expensive part (~5x a 3-sphere trace); gathering hits before entering it
 // keeps its lanes full, and lanes that drift apart (a bounce ray that hits something)
 // fall back into step on the next round instead of staying out of phase for the rest of
@@ -227,12 +302,9 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
     if (inside && !p.zeroFirst)
         acc = p.accum[pixel];
 
-    V3 d0 = { 0.0f, 0.0f, 0.0f };
-    if (inside)
-        d0 = primary_direction(p.cam, x, y, p.width, p.height);
-
     uint32_t j = 0; // frames done
     uint32_t frame = p.firstFrame;
+    uint32_t rays = 0, traced = 0;
     bool alive = inside && p.nFrames > 0;
     if (alive && p.maxBounces < 1)
     {
@@ -241,29 +313,76 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
         alive = false;
     }
 
+    // primary ray and its hit, once per launch
+    V3 d0 = { 0.0f, 0.0f, 0.0f };
+    float tPrimary = 0.0f;
+    int cPrimary = -1;
+    if (alive)
+    {
+        d0 = primary_direction(p.cam, x, y, p.width, p.height);
+        float tmin = 3.402823466e+38f; // FLT_MAX
+        const RayConst rk = ray_constants(d0.x, d0.y, d0.z);
+        trace_range(sphS, p.nSpheres, 0u, p.cam.pos[0], p.cam.pos[1], p.cam.pos[2], d0.x, d0.y, d0.z, rk, tmin, cPrimary);
+        tPrimary = tmin;
+        traced++;
+        if (cPrimary < 0)
+        {
+            accumulate_sky(p, acc, p.nFrames);
+            rays += p.nFrames;
+            j = p.nFrames;
+            alive = false;
+        }
+    }
+
     PathState s;
     path_begin(s, p.cam.pos, d0, pixel, frame);
-    bool pending = false;
-    float tminP = 0.0f;
-    int closestP = -1;
-    uint32_t rays = 0;
+    bool pending = alive; // the primary hit of the first frame is parked
+    float tminP = tPrimary;
+    int closestP = cPrimary;
+    if (alive)
+        rays++;
 
-    // the sample is complete: add it and start the next frame's path, or retire the lane
+    // the sample is complete: add it and start the next frame's path from the cached primary
+    // hit, or retire the lane
     auto finish = [&]() {
         accumulate_sample(acc, s);
         j++;
         if (j >= p.nFrames)
+        {
             alive = false;
+            pending = false;
+        }
         else
         {
             frame += p.frameStride;
             path_begin(s, p.cam.pos, d0, pixel, frame);
+            pending = true;
+            tminP = tPrimary;
+            closestP = cPrimary;
+            rays++;
         }
     };
 
     while (__any_sync(kFull, alive))
     {
-        // ---- phase A: closest-hit rounds ----
+        // ---- phase B: one bounce for every parked hit ----
+        if (pending)
+        {
+            pending = false;
+            if (path_hit(p, s, sphS[closestP], closestP, tminP))
+            {
+                float tmin = 3.402823466e+38f;
+                int closest = -1;
+                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+                rays++;
+                traced++;
+                path_shadow(p, s, closest, tmin);
+            }
+            if (path_bounce(p, s))
+                finish();
+        }
+        // ---- phase A: closest-hit rounds for the bounce rays ----
 #pragma unroll 1
         for (uint32_t round = 0; round < p.traceRounds; round++)
         {
@@ -272,11 +391,12 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
                 break;
             if (act)
             {
-                float tmin = 3.402823466e+38f; // FLT_MAX
+                float tmin = 3.402823466e+38f;
                 int closest = -1;
                 const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
                 trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
                 rays++;
+                traced++;
                 if (closest < 0)
                 {
                     path_miss(p, s);
@@ -290,24 +410,6 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
                 }
             }
         }
-        // ---- phase B: one bounce for every parked hit ----
-        if (pending)
-        {
-            pending = false;
-            bool ends = false;
-            if (path_hit(p, s, sphS[closestP], closestP, tminP))
-            {
-                float tmin = 3.402823466e+38f;
-                int closest = -1;
-                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
-                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
-                rays++;
-                path_shadow(p, s, closest, tmin);
-            }
-            ends = path_bounce(p, s);
-            if (ends)
-                finish();
-        }
     }
 
     if (inside)
@@ -316,19 +418,19 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
         if (p.emitRgba)
             p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
     }
-    count_rays(p, rays, j);
+    count_rays(p, rays, traced, j);
 }
 
 // ---------------------------------------------------------------------------
 // Megakernel, two-slot packed form (large scenes: the sphere loop dominates).
 //
 // One thread = two adjacent pixels = two path slots. The path loop of
-// Renderer::perPixel is flattened: every iteration traces ONE ray per slot (closest hit
-// or shadow, whichever that slot's path needs next) against all spheres with the packed
-// f32x2 loop (trace_range2), then runs the matching half of the bounce per slot. A slot
-// whose path ends adds its sample and starts the next frame's path in the same
-// iteration, so both lanes of every packed instruction carry a live ray until the slot's
-// last frame.
+// Renderer::perPixel is flattened: every iteration traces ONE ray per slot (shadow or
+// closest hit, whichever that slot's path needs next) against all spheres with the
+// packed f32x2 loop (trace_range2), then runs the matching half of the bounce per slot.
+// A slot whose path ends adds its sample and starts the next frame's path from the cached
+// primary hit in the same iteration, so both lanes of every packed instruction carry a
+// live ray until the slot's last frame.
 //
 // kChunked: the sphere array does not fit the shared-memory budget; the CTA walks it in
 // double-buffered chunks in lockstep, which needs the outer loop to be CTA-uniform
@@ -339,20 +441,23 @@ struct Slot
     PathState s;
     float4 acc;
     V3 d0;
+    float tPrimary;
+    int cPrimary;
     uint32_t pixel;
     uint32_t j;      // frames done
     uint32_t frame;
+    bool inside;
     bool alive;
     bool shadow;     // the ray in flight is a shadow ray
 };
 
 __device__ __forceinline__ void slot_init(const RenderParams& p, Slot& t, uint32_t x, uint32_t y)
 {
-    const bool inside = x < p.width && y < p.height;
+    t.inside = x < p.width && y < p.height;
     t.pixel = x + y * p.width;
     t.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     t.d0 = { 0.0f, 0.0f, 0.0f };
-    if (inside)
+    if (t.inside)
     {
         if (!p.zeroFirst)
             t.acc = p.accum[t.pixel];
@@ -360,34 +465,62 @@ __device__ __forceinline__ void slot_init(const RenderParams& p, Slot& t, uint32
     }
     t.j = 0;
     t.frame = p.firstFrame;
-    t.alive = inside && p.nFrames > 0;
+    t.alive = t.inside && p.nFrames > 0;
     t.shadow = false;
+    t.tPrimary = 0.0f;
+    t.cPrimary = -1;
     if (t.alive && p.maxBounces < 1)
     {
         accumulate_black(t.acc, p.nFrames);
         t.j = p.nFrames;
         t.alive = false;
     }
-    path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
+    path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame); // the primary ray, traced once in the prologue
 }
 
-__device__ __forceinline__ void slot_finish(const RenderParams& p, Slot& t)
+// Start frame t.frame's path from the cached primary hit and run it up to its next trace:
+// on return the slot has a shadow or bounce ray in flight, or is retired. (Loops only when
+// paths end before any trace: no lights and roulette / bounce limit at the first bounce.)
+template <bool kChunked>
+__device__ __forceinline__ void slot_resume(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays)
+{
+    const float4 sp = kChunked ? __ldg(p.spheres + t.cPrimary) : sphS[t.cPrimary];
+    while (true)
+    {
+        if (t.j >= p.nFrames)
+        {
+            t.alive = false;
+            return;
+        }
+        path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
+        rays++; // the primary traceRay call this path starts with
+        if (path_hit(p, t.s, sp, t.cPrimary, t.tPrimary))
+        {
+            t.shadow = true;
+            return;
+        }
+        t.shadow = false;
+        if (!path_bounce(p, t.s))
+            return;
+        accumulate_sample(t.acc, t.s);
+        t.j++;
+        t.frame += p.frameStride;
+    }
+}
+
+template <bool kChunked>
+__device__ __forceinline__ void slot_finish(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays)
 {
     accumulate_sample(t.acc, t.s);
     t.j++;
-    t.shadow = false;
-    if (t.j >= p.nFrames)
-        t.alive = false;
-    else
-    {
-        t.frame += p.frameStride;
-        path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
-    }
+    t.frame += p.frameStride;
+    slot_resume<kChunked>(p, t, sphS, rays);
 }
 
 // the half-bounce that follows the trace of this slot's ray
 template <bool kChunked>
-__device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, const float4* sphS, int closest, float tmin)
+__device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, const float4* sphS, int closest, float tmin,
+                                             uint32_t& rays)
 {
     bool bounce = false;
     if (!t.shadow)
@@ -395,7 +528,7 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
         if (closest < 0)
         {
             path_miss(p, t.s);
-            slot_finish(p, t);
+            slot_finish<kChunked>(p, t, sphS, rays);
             return;
         }
         const float4 sp = kChunked ? __ldg(p.spheres + closest) : sphS[closest];
@@ -411,14 +544,53 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
         bounce = true;
     }
     if (bounce && path_bounce(p, t.s))
-        slot_finish(p, t);
+        slot_finish<kChunked>(p, t, sphS, rays);
+}
+
+// one ray per slot against the whole scene
+template <bool kChunked>
+__device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* sphS, uint32_t* candS, const Slot& a,
+                                           const Slot& b, float& tmin0, int& closest0, float& tmin1, int& closest1)
+{
+    tmin0 = tmin1 = 3.402823466e+38f; // FLT_MAX
+    closest0 = closest1 = -1;
+    const RayConst k0 = ray_constants(a.s.dx, a.s.dy, a.s.dz);
+    const RayConst k1 = ray_constants(b.s.dx, b.s.dy, b.s.dz);
+    RayPair rp;
+    rp.ox = pk2(a.s.ox, b.s.ox); rp.oy = pk2(a.s.oy, b.s.oy); rp.oz = pk2(a.s.oz, b.s.oz);
+    rp.dx = pk2(a.s.dx, b.s.dx); rp.dy = pk2(a.s.dy, b.s.dy); rp.dz = pk2(a.s.dz, b.s.dz);
+    rp.na = pk2(fneg(k0.a), fneg(k1.a));
+    if (!kChunked)
+    {
+        trace_range2(sphS, p.nSpheres, 0u, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
+    }
+    else
+    {
+        // double-buffered chunk walk; all threads of the CTA take part in staging
+        const uint32_t C = p.chunkSpheres, stride = round_up8(C);
+        const uint32_t nChunks = (p.nSpheres + C - 1) / C;
+        float4* buf = const_cast<float4*>(sphS);
+        stage_spheres(buf, p.spheres, min(C, p.nSpheres));
+        for (uint32_t c = 0; c < nChunks; c++)
+        {
+            __syncthreads(); // chunk c is resident
+            const float4* cur = buf + (c & 1u) * stride;
+            if (c + 1 < nChunks)
+                stage_spheres(buf + ((c + 1) & 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C));
+            if (a.alive || b.alive)
+                trace_range2(cur, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
+                             tmin0, closest0, tmin1, closest1);
+        }
+        __syncthreads(); // nobody still reads the buffers when the next trace restages
+    }
 }
 
 template <bool kChunked>
 __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
 {
     extern __shared__ float4 smem[];
-    float4* sphS = smem;
+    uint32_t* candS = reinterpret_cast<uint32_t*>(smem); // candWords x blockDim.x candidate words
+    float4* sphS = smem + cand_words(p) * 256u / 4u;
 
     uint32_t x, y;
     thread_pixel_pair(x, y);
@@ -432,66 +604,79 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
     Slot a, b;
     slot_init(p, a, x, y);
     slot_init(p, b, x + 1u, y);
-    uint32_t rays = 0;
+    uint32_t rays = 0, traced = 0;
+
+    // ---- prologue: the primary rays, once per launch ----
+    if (kChunked ? __syncthreads_or(a.alive || b.alive) : (a.alive || b.alive))
+    {
+        float tmin0, tmin1;
+        int closest0, closest1;
+        trace_pair<kChunked>(p, sphS, candS, a, b, tmin0, closest0, tmin1, closest1);
+        if (a.alive)
+        {
+            traced++;
+            a.tPrimary = tmin0;
+            a.cPrimary = closest0;
+            if (closest0 < 0)
+            {
+                accumulate_sky(p, a.acc, p.nFrames);
+                rays += p.nFrames;
+                a.j = p.nFrames;
+                a.alive = false;
+            }
+            else
+                slot_resume<kChunked>(p, a, sphS, rays);
+        }
+        if (b.alive)
+        {
+            traced++;
+            b.tPrimary = tmin1;
+            b.cPrimary = closest1;
+            if (closest1 < 0)
+            {
+                accumulate_sky(p, b.acc, p.nFrames);
+                rays += p.nFrames;
+                b.j = p.nFrames;
+                b.alive = false;
+            }
+            else
+                slot_resume<kChunked>(p, b, sphS, rays);
+        }
+    }
 
     while (kChunked ? __syncthreads_or(a.alive || b.alive) : (a.alive || b.alive))
     {
         // ---- trace the ray in flight of each slot against every sphere (Renderer::traceRay) ----
-        float tmin0 = 3.402823466e+38f, tmin1 = 3.402823466e+38f; // FLT_MAX
-        int closest0 = -1, closest1 = -1;
-        const RayConst k0 = ray_constants(a.s.dx, a.s.dy, a.s.dz);
-        const RayConst k1 = ray_constants(b.s.dx, b.s.dy, b.s.dz);
-        RayPair rp;
-        rp.ox = pk2(a.s.ox, b.s.ox); rp.oy = pk2(a.s.oy, b.s.oy); rp.oz = pk2(a.s.oz, b.s.oz);
-        rp.dx = pk2(a.s.dx, b.s.dx); rp.dy = pk2(a.s.dy, b.s.dy); rp.dz = pk2(a.s.dz, b.s.dz);
-        rp.na = pk2(fneg(k0.a), fneg(k1.a));
-        if (!kChunked)
-        {
-            trace_range2(sphS, p.nSpheres, 0u, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
-        }
-        else
-        {
-            // double-buffered chunk walk; all threads of the CTA take part in staging
-            const uint32_t C = p.chunkSpheres, stride = round_up8(C);
-            const uint32_t nChunks = (p.nSpheres + C - 1) / C;
-            stage_spheres(sphS, p.spheres, min(C, p.nSpheres));
-            for (uint32_t c = 0; c < nChunks; c++)
-            {
-                __syncthreads(); // chunk c is resident
-                const float4* cur = sphS + (c & 1u) * stride;
-                if (c + 1 < nChunks)
-                    stage_spheres(sphS + ((c + 1) & 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C));
-                if (a.alive || b.alive)
-                    trace_range2(cur, min(C, p.nSpheres - c * C), c * C, rp, a.s, b.s, a.alive, b.alive, k0, k1,
-                                 tmin0, closest0, tmin1, closest1);
-            }
-            __syncthreads(); // nobody still reads the buffers when the next iteration restages
-        }
+        float tmin0, tmin1;
+        int closest0, closest1;
+        trace_pair<kChunked>(p, sphS, candS, a, b, tmin0, closest0, tmin1, closest1);
         if (a.alive)
         {
             rays++;
-            slot_advance<kChunked>(p, a, sphS, closest0, tmin0);
+            traced++;
+            slot_advance<kChunked>(p, a, sphS, closest0, tmin0, rays);
         }
         if (b.alive)
         {
             rays++;
-            slot_advance<kChunked>(p, b, sphS, closest1, tmin1);
+            traced++;
+            slot_advance<kChunked>(p, b, sphS, closest1, tmin1, rays);
         }
     }
 
-    if (x < p.width && y < p.height)
+    if (a.inside)
     {
         p.accum[a.pixel] = a.acc;
         if (p.emitRgba)
             p.rgba[a.pixel] = pack_rgba8(a.acc, u32_to_f32_rn(p.rgbaDivisor));
-        if (x + 1u < p.width)
-        {
-            p.accum[b.pixel] = b.acc;
-            if (p.emitRgba)
-                p.rgba[b.pixel] = pack_rgba8(b.acc, u32_to_f32_rn(p.rgbaDivisor));
-        }
     }
-    count_rays(p, rays, a.j + b.j);
+    if (b.inside)
+    {
+        p.accum[b.pixel] = b.acc;
+        if (p.emitRgba)
+            p.rgba[b.pixel] = pack_rgba8(b.acc, u32_to_f32_rn(p.rgbaDivisor));
+    }
+    count_rays(p, rays, traced, a.j + b.j);
 }
 
 // ---------------------------------------------------------------------------
@@ -568,7 +753,8 @@ size_t megakernel_smem_bytes(const RenderParams& p)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
     const size_t pad8 = (static_cast<size_t>(chunked ? p.chunkSpheres : p.nSpheres) + 7u) & ~size_t(7);
-    return sizeof(float4) * (chunked ? 2 * pad8 : pad8);
+    // the two-slot form also keeps cand_words() candidate words per thread (sized for both forms)
+    return sizeof(float4) * (chunked ? 2 * pad8 : pad8) + sizeof(uint32_t) * cand_words(p) * 256u;
 }
 
 cudaError_t configure()

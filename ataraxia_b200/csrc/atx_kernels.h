@@ -14,7 +14,7 @@ namespace atx_launch
 // dynamic shared memory the megakernel may opt in to (227 KB is the sm_100 per-CTA limit;
 // the default budget keeps two CTAs resident per SM)
 constexpr int kMaxSmemBytes = 227 * 1024;
-constexpr int kSmemBudgetTwoCtas = 100 * 1024;
+constexpr int kSmemBudgetTwoCtas = 72 * 1024; // sphere records; + 32 KB candidate words + 1 KB reserve, twice, fits 227 KB
 
 // megakernel forms (ATX_TUNE_MEGA_KIND); 0 = by sphere count
 constexpr int kMegaAuto = 0;

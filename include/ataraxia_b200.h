@@ -71,9 +71,13 @@ typedef struct atx_light {    /* == Light, Engine/include/Scene.h:17-26 (28 B) *
 
 typedef struct atx_counters {
     uint64_t paths;           /* perPixel evaluations (pixel x sample) */
-    uint64_t rays;            /* traceRay calls (closest-hit + shadow) */
+    uint64_t rays;            /* traceRay calls of the reference (closest-hit + shadow) */
     uint64_t sphere_tests;    /* rays x numSpheres (brute force, Renderer.cu:256) */
     uint64_t launches;        /* kernels of this library launched on the handle */
+    uint64_t rays_traced;     /* rays whose sphere loop ran on the device: the primary ray of a
+                                 pixel is the same every frame (no jitter, Camera.cpp:176-187), so
+                                 it is traced once per launch and its hit reused by every frame */
+    uint64_t sphere_tests_executed; /* rays_traced x numSpheres: what the roofline is computed from */
 } atx_counters;
 
 /* kernel family for atx_render* */

@@ -11,12 +11,7 @@ except Exception as e:
     print("$name failed", e); print(open("gpurun_out/exp/$name.err").read()[-600:])
 PY
 }
-b c2_ww1 --workload c2 --mega-kind 1 --trace-rounds 1
-b c2_ww2 --workload c2 --mega-kind 1 --trace-rounds 2
-b c2_ww3 --workload c2 --mega-kind 1 --trace-rounds 3
-b c2_ww4 --workload c2 --mega-kind 1 --trace-rounds 4
-b c2_pair --workload c2 --mega-kind 2
-b c3_pair --workload c3 --spp 64
-b c3_ww --workload c3 --spp 64 --mega-kind 1
-b c4_pair --workload c4 --spp 16
-b c4_chunk --workload c4 --spp 16 --chunk 2048
+for spec in "$@"; do
+  name=${spec%%:*}; args=${spec#*:}
+  b $name $args
+done
