@@ -27,7 +27,7 @@ SYMBOLS = [
 ATX_OK = 0
 ATX_ERR_INVALID, ATX_ERR_CUDA, ATX_ERR_NCCL, ATX_ERR_NO_DEVICE, ATX_ERR_ALLOC = -1, -2, -3, -4, -5
 VARIANT_AUTO, VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1, 2
-TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_TRACE_ROUNDS = 1, 2, 3
+TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD = 1, 2, 3, 4
 MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR = 0, 1, 2
 
 # numpy views of the reference PODs (SceneNode.h:11-21, Scene.h:17-47)

@@ -121,6 +121,8 @@ struct atx_renderer
     int32_t* dHit = nullptr;   // lazily allocated debug buffers
     float* dRays = nullptr;
     unsigned long long* dCounters = nullptr;
+    uint32_t* dPool = nullptr;  // pixel-pool counter of the persistent megakernels
+    int smCount = 0;
 
     // scene
     float *dSphAoS = nullptr, *dMatAoS = nullptr, *dLightAoS = nullptr;
@@ -136,7 +138,8 @@ struct atx_renderer
     uint32_t lastFrame = 1;     // frameIndex of the last rendered frame (display divisor)
     uint32_t chunkOverride = 0; // tuning: force the shared-memory chunk size (spheres)
     int megaKind = 0;           // tuning: 0 = by sphere count, 1 = while-while, 2 = two-slot packed
-    uint32_t traceRounds = 2;   // tuning: closest-hit rounds per shading phase (while-while form)
+    uint32_t parkThreshold = 8;  // tuning: parked hits per warp that trigger the bounce phase (while-while form)
+    uint32_t claimThreshold = 0; // tuning: idle lanes per warp that trigger a batched pixel claim (0 = per form)
     uint64_t launches = 0;
 
     ncclComm_t comm = nullptr;
@@ -174,7 +177,9 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
     else if (h->nS > fit)
         chunk = fit / 2; // double-buffered
     p.chunkSpheres = chunk ? chunk : 1;
-    p.traceRounds = h->traceRounds;
+    p.parkThreshold = h->parkThreshold;
+    p.poolSize = ((h->width + 7u) / 8u) * ((h->height + 3u) / 4u) * 32u;
+    p.pool = h->dPool;
     const atx::mat4& ip = h->cam.invProj;
     const atx::mat4& iv = h->cam.invView;
     for (int i = 0; i < 4; i++)
@@ -246,6 +251,8 @@ atx_status atx_create(int device_ordinal, atx_handle* out)
     ATX_CUDA(cudaEventCreate(&h->evStop));
     ATX_CUDA(cudaMalloc(&h->dCounters, 4 * sizeof(unsigned long long)));
     ATX_CUDA(cudaMemsetAsync(h->dCounters, 0, 4 * sizeof(unsigned long long), h->stream));
+    ATX_CUDA(cudaMalloc(&h->dPool, sizeof(uint32_t)));
+    ATX_CUDA(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, device_ordinal));
     ATX_CUDA(atx_launch::configure());
     *out = h;
     return ATX_OK;
@@ -259,7 +266,7 @@ atx_status atx_destroy(atx_handle h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && nccl().ok)
         nccl().CommDestroy(h->comm);
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters);
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
@@ -394,10 +401,15 @@ atx_status atx_set_tuning(atx_handle h, int key, int64_t value)
             return fail(ATX_ERR_INVALID, "mega_kind must be 0 (auto), 1 (while-while) or 2 (two-slot packed)");
         h->megaKind = static_cast<int>(value);
         return ATX_OK;
-    case ATX_TUNE_TRACE_ROUNDS:
-        if (value < 1 || value > 64)
-            return fail(ATX_ERR_INVALID, "trace_rounds must be in [1, 64]");
-        h->traceRounds = static_cast<uint32_t>(value);
+    case ATX_TUNE_PARK_THRESHOLD:
+        if (value < 1 || value > 32)
+            return fail(ATX_ERR_INVALID, "park_threshold must be in [1, 32]");
+        h->parkThreshold = static_cast<uint32_t>(value);
+        return ATX_OK;
+    case ATX_TUNE_CLAIM_THRESHOLD:
+        if (value < 0 || value > 32)
+            return fail(ATX_ERR_INVALID, "claim_threshold must be in [0, 32] (0 = automatic)");
+        h->claimThreshold = static_cast<uint32_t>(value);
         return ATX_OK;
     default:
         return fail(ATX_ERR_INVALID, "unknown tuning key %d", key);
@@ -438,7 +450,12 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.rgbaDivisor = rgbaDivisor;
     if (atx_launch::megakernel_smem_bytes(p) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
         return fail(ATX_ERR_INVALID, "shared-memory plan exceeds the device limit");
-    ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->stream));
+    // pixel claims: whole 8x4 tiles for the while-while form (its lockstep lives on coherent warps), small
+    // batches for the packed form (the sphere loop does not care which pixels share a warp)
+    p.claimThreshold = h->claimThreshold ? h->claimThreshold
+                                         : (atx_launch::mega_kind(p, h->megaKind) == atx_launch::kMegaWhileWhile ? 32u : 2u);
+    ATX_CUDA(cudaMemsetAsync(h->dPool, 0, sizeof(uint32_t), h->stream));
+    ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->smCount, h->stream));
     h->launches++;
     return ATX_OK;
 }

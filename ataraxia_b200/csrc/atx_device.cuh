@@ -51,7 +51,10 @@ struct RenderParams
     uint32_t rgbaDivisor;   // frameIndex used for the display divide (Renderer.cu:166)
     uint32_t nSpheres, nMaterials, nLights;
     uint32_t chunkSpheres;  // spheres per shared-memory chunk (>= nSpheres: staged once)
-    uint32_t traceRounds;   // while-while kernel: closest-hit rounds before the shading phase
+    uint32_t parkThreshold; // while-while kernel: parked hits (of 32 lanes) that trigger the bounce phase
+    uint32_t claimThreshold; // idle lanes (of 32) that trigger a batched pixel claim
+    uint32_t poolSize;      // pixel ids in the pool: 8x4 tiles x 32, padded tiles included
+    uint32_t* pool;         // next unclaimed id (zeroed before the launch)
     const float4* spheres;
     const int32_t* sphMat;
     const float4* mats;
@@ -309,21 +312,15 @@ ATX_DEV V3 cook_torrance(const float4 m0, const float4 m1, const float4 m2, cons
 // as fma(z, N, fma(x, T, y*B)).
 ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
 {
-    float Tx, Ty, Tz;
-    if (fabs_(N.x) > fabs_(N.y))
-    {
-        const float s = fsqrt_approx(ffma(N.z, N.z, fmul(N.x, N.x)));
-        Tx = fdiv_approx(fneg(N.z), s);
-        Ty = fdiv_approx(0.0f, s);
-        Tz = fdiv_approx(N.x, s);
-    }
-    else
-    {
-        const float s = fsqrt_approx(ffma(N.z, N.z, fmul(N.y, N.y)));
-        Tx = fdiv_approx(0.0f, s);
-        Ty = fdiv_approx(fneg(N.z), s);
-        Tz = fdiv_approx(N.y, s);
-    }
+    // the two branches of the reference differ only in which component of N pairs with N.z;
+    // selecting the operands instead of branching runs the same instructions on the same values
+    const bool xMajor = fabs_(N.x) > fabs_(N.y);
+    const float major = xMajor ? N.x : N.y;
+    const float s = fsqrt_approx(ffma(N.z, N.z, fmul(major, major)));
+    const float nz = fneg(N.z);
+    const float Tx = fdiv_approx(xMajor ? nz : 0.0f, s);
+    const float Ty = fdiv_approx(xMajor ? 0.0f : nz, s);
+    const float Tz = fdiv_approx(major, s);
     // cross(N, T): ptxas fuses the first product of each component (sampler SASS 0x380-0x3d0)
     const float Bx = ffma(N.y, Tz, fneg(fmul(Ty, N.z)));
     const float By = ffma(Tx, N.z, fneg(fmul(N.x, Tz)));
@@ -333,31 +330,33 @@ ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
              ffma(z, N.z, ffma(x, Tz, fmul(y, Bz))) };
 }
 
-// BRDF::sampleHemisphereCosineWeighted (BRDF.cu:72-93)
-ATX_DEV V3 sample_cosine(const V3 N, uint32_t& seed)
+// BRDF::sampleHemisphereCosineWeighted (BRDF.cu:72-93) and BRDF::sampleGGX (BRDF.cu:95-117) in one
+// body: both draw u1, u2, build (r cos phi, r sin phi, z) and go through the same tangent frame; only
+// r and z differ, so a warp with both kinds of material shares everything but two short selects.
+//   cosine: r = sqrt(u1), z = sqrt(1 - u1)
+//   GGX   : z = sqrt((1 - u1) / fma(ggxT, u1, 1)), r = sqrt(fma(-z, z, 1)), ggxT = fma(a, a, -1), a = roughness^2
+//           (1 - cos^2 is contracted by ptxas, sampler SASS 0x2d0). The half-vector itself is returned as
+//           the new direction (reference quirk Q-ggx).
+ATX_DEV V3 sample_direction(const V3 N, bool ggx, float ggxT, uint32_t& seed)
 {
     const float u1 = pcg_float(seed);
     const float u2 = pcg_float(seed);
-    const float r = fsqrt_approx(u1);
-    const float theta = fmul(u2, 6.28318548f);
-    const float x = fmul(r, fcos_approx(theta));
-    const float y = fmul(r, fsin_approx(theta));
-    const float z = fsqrt_approx(fsub(1.0f, u1));
-    return to_world(N, x, y, z);
-}
-
-// BRDF::sampleGGX (BRDF.cu:95-117); ggxT = fma(a, a, -1) with a = roughness^2. The
-// half-vector itself is returned as the new direction (reference quirk Q-ggx).
-ATX_DEV V3 sample_ggx(const V3 N, float ggxT, uint32_t& seed)
-{
-    const float u1 = pcg_float(seed);
-    const float u2 = pcg_float(seed);
-    const float cosT = fsqrt_approx(fdiv_approx(fsub(1.0f, u1), ffma(ggxT, u1, 1.0f)));
-    const float sinT = fsqrt_approx(ffma(fneg(cosT), cosT, 1.0f)); // 1 - cos^2, contracted by ptxas (SASS 0x2d0)
+    const float omu = fsub(1.0f, u1);
+    float r, z;
+    if (ggx)
+    {
+        z = fsqrt_approx(fdiv_approx(omu, ffma(ggxT, u1, 1.0f)));
+        r = fsqrt_approx(ffma(fneg(z), z, 1.0f));
+    }
+    else
+    {
+        r = fsqrt_approx(u1);
+        z = fsqrt_approx(omu);
+    }
     const float phi = fmul(u2, 6.28318548f);
-    const float x = fmul(sinT, fcos_approx(phi));
-    const float y = fmul(sinT, fsin_approx(phi));
-    return to_world(N, x, y, cosT);
+    const float x = fmul(r, fcos_approx(phi));
+    const float y = fmul(r, fsin_approx(phi));
+    return to_world(N, x, y, z);
 }
 
 // kernelRender's display pack (Renderer.cu:166-168; colorUtils::vec4ToRGBA, Renderer.h:70-78)
@@ -441,7 +440,7 @@ ATX_DEV bool path_hit(const RenderParams& p, PathState& s, const float4 sp, int 
     if (p.nLights > 0)
     {
         // light pick reuses the un-advanced seed (Renderer.cu:340)
-        s.lightIndex = pcg_hash(s.seed) % p.nLights;
+        s.lightIndex = p.nLights == 1u ? 0u : pcg_hash(s.seed) % p.nLights; // x % 1 == 0: skip the hash
         const float4 lp = __ldg(p.lights + kLightStride * s.lightIndex);
         const float lx = fsub(lp.x, wp.x), ly = fsub(lp.y, wp.y), lz = fsub(lp.z, wp.z);
         s.dist2 = fdot3(lx, ly, lz, lx, ly, lz);
@@ -487,11 +486,9 @@ ATX_DEV bool path_bounce(const RenderParams& p, PathState& s)
     if (pcg_float(s.seed) > pr)
         return true;
     s.tx = fdiv_approx(s.tx, pr); s.ty = fdiv_approx(s.ty, pr); s.tz = fdiv_approx(s.tz, pr);
-    V3 nd;
-    if (m1.w > 0.0f)
-        nd = sample_ggx(s.N, __ldg(p.mats + kMatStride * s.matIndex + 5).x, s.seed);
-    else
-        nd = sample_cosine(s.N, s.seed);
+    const bool ggx = m1.w > 0.0f; // metallic > 0 (Renderer.cu:381-384)
+    const float ggxT = ggx ? __ldg(p.mats + kMatStride * s.matIndex + 5).x : 0.0f;
+    const V3 nd = sample_direction(s.N, ggx, ggxT, s.seed);
     s.dx = nd.x; s.dy = nd.y; s.dz = nd.z;
     s.bounce++;
     if (s.bounce >= p.maxBounces)

@@ -202,13 +202,40 @@ __device__ __forceinline__ void thread_pixel(uint32_t& x, uint32_t& y)
     y = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
 }
 
-// two horizontally adjacent pixels per thread (x, y) and (x+1, y): a CTA covers 64x8, a warp
-// 16x4; a thread's two float4 accumulators are 32 contiguous bytes.
-__device__ __forceinline__ void thread_pixel_pair(uint32_t& x, uint32_t& y)
+// ---------------------------------------------------------------------------
+// Pixel pool. Paths differ in length from pixel to pixel, so a fixed pixel-to-lane map
+// leaves lanes idle while the slowest pixel of their warp finishes (measured: 17 of 32
+// lanes active on config 2). Both megakernels therefore run as persistent CTAs whose
+// lanes CLAIM pixels from one global counter: ids are handed out in 8x4-tile order (32
+// consecutive ids = one tile, so a full-warp claim is one coherent tile), a lane keeps a
+// pixel for all its frames (the frame order of the float4 sum is what makes the result
+// bit-identical to the reference), stores the 16 B result itself and claims the next id.
+// Claims are batched per warp (at least claimThreshold idle lanes, or nothing left to do)
+// so the per-pixel prologue runs with several lanes active. Which lane renders which pixel
+// never changes a result.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool pool_pixel(const RenderParams& p, uint32_t id, uint32_t& x, uint32_t& y)
 {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    x = blockIdx.x * 64u + (warp & 3u) * 16u + (lane & 7u) * 2u;
-    y = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
+    const uint32_t tilesX = (p.width + 7u) >> 3;
+    const uint32_t tile = id >> 5, w = id & 31u;
+    x = (tile % tilesX) * 8u + (w & 7u);
+    y = (tile / tilesX) * 4u + (w >> 3);
+    return x < p.width && y < p.height;
+}
+
+// warp-aggregated claim: one atomic per warp; returns this lane's id (valid where need is set)
+__device__ __forceinline__ uint32_t pool_claim(uint32_t* counter, bool need)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (mask == 0u)
+        return 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0u;
+    if (static_cast<int>(lane) == leader)
+        base = atomicAdd(counter, static_cast<uint32_t>(__popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void count_rays(const RenderParams& p, uint32_t rays, uint32_t traced, uint32_t paths)
@@ -258,8 +285,8 @@ __device__ __forceinline__ void accumulate_sky(const RenderParams& p, float4& ac
 // The primary ray of a pixel is the same every frame: Camera::UpdateRayDirection has no
 // jitter and no half-pixel offset (Camera.cpp:176-187), and ray.origin is the camera
 // position (Renderer.cu:291-293). Its traceRay result (t, sphere) is therefore a per-pixel
-// constant of the launch: both megakernel forms trace it once in their prologue and start
-// every frame's path from that hit record. The first traceRay call of frames 2..n is not
+// constant of the launch: a lane traces it once when it claims the pixel and starts every
+// frame's path from that hit record. The first traceRay call of frames 2..n is not
 // executed; `rays` still counts it (it is a traceRay call of the reference), `traced`
 // counts the rays whose sphere loop really ran (the roofline uses `traced`).
 // ---------------------------------------------------------------------------
@@ -267,170 +294,257 @@ __device__ __forceinline__ void accumulate_sky(const RenderParams& p, float4& ac
 // ---------------------------------------------------------------------------
 // Megakernel, while-while form (small scenes: shading dominates the sphere loop).
 //
-// One thread = one pixel, all requested frames f = firstFrame + j*frameStride of it. The
-// warp alternates between two phases:
-//   B  lanes with a parked hit run the whole bounce in lockstep: hit record, emission,
-//      light pick, shadow trace, Cook-Torrance, Russian roulette, next direction;
-//   A  lanes with a bounce ray in flight trace it; a miss ends the path, adds the sample
-//      to the running sum and starts the next frame's path at once (path regeneration) -
-//      which parks the cached primary hit; a hit is parked. Up to traceRounds rounds, or
-//      until every live lane has a hit parked.
-// Phase B is the expensive part (~5x a 3-sphere trace); gathering hits before entering it
-// keeps its lanes full, and lanes that drift apart (a bounce ray that hits something)
-// fall back into step on the next round instead of staying out of phase for the rest of
-// the launch. The samples of a pixel are summed in registers in frame order, so the
-// float4 sums are bit-identical to sequential reference frames, and the accumulation
-// buffer is touched once: one 16 B read + one 16 B write per pixel per launch.
+// One lane = one claimed pixel, all requested frames f = firstFrame + j*frameStride of it.
+// A lane is either "in flight" (its path has a ray to trace) or "parked" (a hit is waiting
+// for its bounce). The warp alternates between two phases:
+//   A  in-flight lanes trace their ray; a miss ends the path, adds the sample to the
+//      running sum and starts the next frame's path at once (path regeneration); a hit is
+//      parked;
+//   B  parked lanes run the whole bounce in lockstep: hit record, emission, light pick,
+//      shadow trace, Cook-Torrance, Russian roulette, next direction.
+// Phase B is the expensive part (~5x a 3-sphere trace). It runs when at least
+// `parkThreshold` lanes are parked or nothing is in flight, so its lanes are full, and
+// lanes that drift apart fall back into step instead of staying out of phase for the
+// rest of the launch. A freshly claimed pixel needs no code of its own: its primary ray
+// goes through phase A and its primary hit through phase B like any other (`fresh`).
+//
+// kFixedLight (numLights <= 1): the light pick "PcgHash(seed) % numLights" (Renderer.cu:340)
+// is 0 for every seed, so the whole first bounce up to the roulette - hit record,
+// emission, shadow ray, Cook-Torrance - is the same for every frame of a pixel. It runs
+// once (the fresh pass) and every frame's path starts from that state (color, next
+// origin, normal, material) with its own seed; only path_bounce onwards runs per frame.
+//
+// The samples of a pixel are summed in registers in frame order, so the float4 sums are
+// bit-identical to sequential reference frames, and the accumulation buffer is touched
+// once: one 16 B read + one 16 B write per pixel per launch.
 // ---------------------------------------------------------------------------
+template <bool kFixedLight>
 __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 {
     extern __shared__ float4 smem[];
     float4* sphS = smem;
     constexpr unsigned kFull = 0xffffffffu;
 
-    uint32_t x, y;
-    thread_pixel(x, y);
-    const bool inside = x < p.width && y < p.height;
-    const uint32_t pixel = x + y * p.width;
-
     stage_spheres(sphS, p.spheres, p.nSpheres);
     __syncthreads();
 
-    // running sum starts from the stored value so the additions happen in the same
-    // order as the reference's per-frame "accumulation[p] += color" (Renderer.cu:165)
+    // lane state
+    bool alive = false;     // owns a pixel with frames left
+    bool parked = false;    // a hit waits for its bounce (tminP, closestP)
+    bool fresh = false;     // the ray in flight / hit parked is the pixel's primary
+    bool exhausted = false; // the pool has no more pixels
+    uint32_t pixel = 0, j = 0, frame = 0;
     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (inside && !p.zeroFirst)
-        acc = p.accum[pixel];
-
-    uint32_t j = 0; // frames done
-    uint32_t frame = p.firstFrame;
-    uint32_t rays = 0, traced = 0;
-    bool alive = inside && p.nFrames > 0;
-    if (alive && p.maxBounces < 1)
-    {
-        accumulate_black(acc, p.nFrames);
-        j = p.nFrames;
-        alive = false;
-    }
-
-    // primary ray and its hit, once per launch
     V3 d0 = { 0.0f, 0.0f, 0.0f };
-    float tPrimary = 0.0f;
-    int cPrimary = -1;
-    if (alive)
-    {
-        d0 = primary_direction(p.cam, x, y, p.width, p.height);
-        float tmin = 3.402823466e+38f; // FLT_MAX
-        const RayConst rk = ray_constants(d0.x, d0.y, d0.z);
-        trace_range(sphS, p.nSpheres, 0u, p.cam.pos[0], p.cam.pos[1], p.cam.pos[2], d0.x, d0.y, d0.z, rk, tmin, cPrimary);
-        tPrimary = tmin;
-        traced++;
-        if (cPrimary < 0)
-        {
-            accumulate_sky(p, acc, p.nFrames);
-            rays += p.nFrames;
-            j = p.nFrames;
-            alive = false;
-        }
-    }
-
     PathState s;
-    path_begin(s, p.cam.pos, d0, pixel, frame);
-    bool pending = alive; // the primary hit of the first frame is parked
-    float tminP = tPrimary;
-    int closestP = cPrimary;
-    if (alive)
-        rays++;
+    path_begin(s, p.cam.pos, d0, 0u, 0u);
+    s.N = s.V = d0;
+    s.dist2 = 0.0f;
+    s.matIndex = 0;
+    s.lightIndex = 0u;
+    float tminP = 0.0f, tPrimary = 0.0f;
+    int closestP = -1, cPrimary = -1;
+    uint32_t raysPerStart = 1; // reference traceRay calls a cached start stands for
+    // kFixedLight: path state after the first bounce's shading
+    float c0r = 0.0f, c0g = 0.0f, c0b = 0.0f, o0x = 0.0f, o0y = 0.0f, o0z = 0.0f;
+    V3 N0 = { 0.0f, 0.0f, 0.0f };
+    int mat0 = 0;
+    uint32_t rays = 0, traced = 0, paths = 0;
 
-    // the sample is complete: add it and start the next frame's path from the cached primary
-    // hit, or retire the lane
+    auto trace = [&](float& tmin, int& closest) {
+        tmin = 3.402823466e+38f; // FLT_MAX
+        closest = -1;
+        const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+        trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+        traced++;
+    };
+    // the pixel is complete: st.global.v4.f32 of the running sum (+ the display pack)
+    auto retire = [&]() {
+        p.accum[pixel] = acc;
+        if (p.emitRgba)
+            p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
+        paths += j;
+        alive = false;
+        parked = false;
+    };
+    // Start frame `frame`'s path and run it to its first per-frame trace: on return the lane is
+    // parked, in flight, or has retired its pixel. (kFixedLight loops only when a path ends at
+    // its first roulette / bounce limit.)
+    auto start = [&]() {
+        while (true)
+        {
+            if (j >= p.nFrames)
+            {
+                retire();
+                return;
+            }
+            rays += raysPerStart;
+            if (!kFixedLight)
+            {
+                path_begin(s, p.cam.pos, d0, pixel, frame);
+                parked = true;
+                tminP = tPrimary;
+                closestP = cPrimary;
+                return;
+            }
+            s.cr = c0r; s.cg = c0g; s.cb = c0b;
+            s.ox = o0x; s.oy = o0y; s.oz = o0z;
+            s.N = N0;
+            s.matIndex = mat0;
+            s.tx = s.ty = s.tz = 1.0f;
+            s.seed = pixel * frame;
+            s.bounce = 0;
+            parked = false;
+            if (!path_bounce(p, s))
+                return;
+            accumulate_sample(acc, s);
+            j++;
+            frame += p.frameStride;
+        }
+    };
     auto finish = [&]() {
         accumulate_sample(acc, s);
         j++;
-        if (j >= p.nFrames)
-        {
-            alive = false;
-            pending = false;
-        }
-        else
-        {
-            frame += p.frameStride;
-            path_begin(s, p.cam.pos, d0, pixel, frame);
-            pending = true;
-            tminP = tPrimary;
-            closestP = cPrimary;
-            rays++;
-        }
+        frame += p.frameStride;
+        start();
     };
 
-    while (__any_sync(kFull, alive))
+    while (true)
     {
-        // ---- phase B: one bounce for every parked hit ----
-        if (pending)
+        // ---- claim pixels for idle lanes ----
+        const unsigned aliveMask = __ballot_sync(kFull, alive);
+        if (aliveMask != kFull)
         {
-            pending = false;
-            if (path_hit(p, s, sphS[closestP], closestP, tminP))
+            const bool need = !alive && !exhausted;
+            const unsigned needMask = __ballot_sync(kFull, need);
+            if (needMask != 0u && (static_cast<uint32_t>(__popc(needMask)) >= p.claimThreshold || aliveMask == 0u))
             {
-                float tmin = 3.402823466e+38f;
-                int closest = -1;
-                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
-                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
-                rays++;
-                traced++;
-                path_shadow(p, s, closest, tmin);
-            }
-            if (path_bounce(p, s))
-                finish();
-        }
-        // ---- phase A: closest-hit rounds for the bounce rays ----
-#pragma unroll 1
-        for (uint32_t round = 0; round < p.traceRounds; round++)
-        {
-            const bool act = alive && !pending;
-            if (!__any_sync(kFull, act))
-                break;
-            if (act)
-            {
-                float tmin = 3.402823466e+38f;
-                int closest = -1;
-                const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
-                trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
-                rays++;
-                traced++;
-                if (closest < 0)
+                const uint32_t id = pool_claim(p.pool, need);
+                uint32_t x, y;
+                if (need)
                 {
-                    path_miss(p, s);
-                    finish();
-                }
-                else
-                {
-                    pending = true;
-                    tminP = tmin;
-                    closestP = closest;
+                    if (id >= p.poolSize)
+                        exhausted = true;
+                    else if (pool_pixel(p, id, x, y))
+                    {
+                        pixel = x + y * p.width;
+                        // running sum starts from the stored value so the additions happen in the same
+                        // order as the reference's per-frame "accumulation[p] += color" (Renderer.cu:165)
+                        acc = p.zeroFirst ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : p.accum[pixel];
+                        j = 0;
+                        frame = p.firstFrame;
+                        if (p.maxBounces < 1)
+                        {
+                            accumulate_black(acc, p.nFrames);
+                            j = p.nFrames;
+                            retire();
+                        }
+                        else
+                        {
+                            d0 = primary_direction(p.cam, x, y, p.width, p.height);
+                            path_begin(s, p.cam.pos, d0, pixel, frame);
+                            alive = true;
+                            fresh = true;
+                            parked = false;
+                        }
+                    }
                 }
             }
+            if (!__any_sync(kFull, alive))
+            {
+                if (__all_sync(kFull, exhausted))
+                    break;
+                continue;
+            }
         }
-    }
 
-    if (inside)
-    {
-        p.accum[pixel] = acc; // st.global.v4.f32, 4 x 128 B contiguous per warp
-        if (p.emitRgba)
-            p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
+        const unsigned parkedMask = __ballot_sync(kFull, parked);
+        const unsigned nParked = __popc(parkedMask);
+        const bool anyFlying = (__ballot_sync(kFull, alive) & ~parkedMask) != 0u;
+        if (nParked >= p.parkThreshold || !anyFlying)
+        {
+            // ---- phase B: one bounce for every parked hit ----
+            if (parked)
+            {
+                parked = false;
+                if (fresh && !kFixedLight)
+                {
+                    tPrimary = tminP;
+                    cPrimary = closestP;
+                    rays++; // the first frame's primary traceRay call
+                    fresh = false;
+                }
+                if (path_hit(p, s, sphS[closestP], closestP, tminP))
+                {
+                    float tmin;
+                    int closest;
+                    trace(tmin, closest);
+                    if (!fresh)
+                        rays++;
+                    path_shadow(p, s, closest, tmin);
+                    if (fresh)
+                        raysPerStart = 2;
+                }
+                else if (fresh)
+                    raysPerStart = 1;
+                if (fresh)
+                {
+                    // kFixedLight: this was the frame-independent first bounce; keep its result
+                    c0r = s.cr; c0g = s.cg; c0b = s.cb;
+                    o0x = s.ox; o0y = s.oy; o0z = s.oz;
+                    N0 = s.N;
+                    mat0 = s.matIndex;
+                    fresh = false;
+                    start();
+                }
+                else if (path_bounce(p, s))
+                    finish();
+            }
+        }
+        else if (alive && !parked)
+        {
+            // ---- phase A: trace the ray in flight ----
+            float tmin;
+            int closest;
+            trace(tmin, closest);
+            if (!fresh)
+                rays++;
+            if (closest >= 0)
+            {
+                parked = true;
+                tminP = tmin;
+                closestP = closest;
+            }
+            else if (fresh)
+            {
+                // the primary ray misses: every frame of this pixel is a bounce-0 miss
+                accumulate_sky(p, acc, p.nFrames);
+                rays += p.nFrames;
+                j = p.nFrames;
+                fresh = false;
+                retire();
+            }
+            else
+            {
+                path_miss(p, s);
+                finish();
+            }
+        }
     }
-    count_rays(p, rays, traced, j);
+    count_rays(p, rays, traced, paths);
 }
 
 // ---------------------------------------------------------------------------
 // Megakernel, two-slot packed form (large scenes: the sphere loop dominates).
 //
-// One thread = two adjacent pixels = two path slots. The path loop of
-// Renderer::perPixel is flattened: every iteration traces ONE ray per slot (shadow or
-// closest hit, whichever that slot's path needs next) against all spheres with the
-// packed f32x2 loop (trace_range2), then runs the matching half of the bounce per slot.
-// A slot whose path ends adds its sample and starts the next frame's path from the cached
-// primary hit in the same iteration, so both lanes of every packed instruction carry a
-// live ray until the slot's last frame.
+// One thread = two path slots, each rendering a claimed pixel. The path loop of
+// Renderer::perPixel is flattened: every iteration traces ONE ray per slot (primary,
+// shadow or bounce ray, whichever that slot's path needs next) against all spheres with
+// the packed f32x2 loop (trace_range2), then runs the matching half of the bounce per
+// slot. A slot whose path ends adds its sample and starts the next frame's path from the
+// cached primary hit in the same iteration; a slot whose pixel is complete stores it and
+// claims another, so both lanes of every packed instruction carry a live ray until the
+// pool is empty.
 //
 // kChunked: the sphere array does not fit the shared-memory budget; the CTA walks it in
 // double-buffered chunks in lockstep, which needs the outer loop to be CTA-uniform
@@ -446,50 +560,61 @@ struct Slot
     uint32_t pixel;
     uint32_t j;      // frames done
     uint32_t frame;
-    bool inside;
     bool alive;
     bool shadow;     // the ray in flight is a shadow ray
+    bool fresh;      // the ray in flight is the pixel's primary ray
 };
 
-__device__ __forceinline__ void slot_init(const RenderParams& p, Slot& t, uint32_t x, uint32_t y)
+__device__ __forceinline__ void slot_retire(const RenderParams& p, Slot& t, uint32_t& paths)
 {
-    t.inside = x < p.width && y < p.height;
-    t.pixel = x + y * p.width;
-    t.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    t.d0 = { 0.0f, 0.0f, 0.0f };
-    if (t.inside)
+    p.accum[t.pixel] = t.acc;
+    if (p.emitRgba)
+        p.rgba[t.pixel] = pack_rgba8(t.acc, u32_to_f32_rn(p.rgbaDivisor));
+    paths += t.j;
+    t.alive = false;
+}
+
+// the slot takes pool pixel `id` (or learns that the pool is empty)
+__device__ __forceinline__ void slot_claim(const RenderParams& p, Slot& t, uint32_t id, bool& exhausted, uint32_t& paths)
+{
+    uint32_t x, y;
+    if (id >= p.poolSize)
     {
-        if (!p.zeroFirst)
-            t.acc = p.accum[t.pixel];
-        t.d0 = primary_direction(p.cam, x, y, p.width, p.height);
+        exhausted = true;
+        return;
     }
+    if (!pool_pixel(p, id, x, y))
+        return;
+    t.pixel = x + y * p.width;
+    t.acc = p.zeroFirst ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : p.accum[t.pixel];
     t.j = 0;
     t.frame = p.firstFrame;
-    t.alive = t.inside && p.nFrames > 0;
-    t.shadow = false;
-    t.tPrimary = 0.0f;
-    t.cPrimary = -1;
-    if (t.alive && p.maxBounces < 1)
+    if (p.maxBounces < 1)
     {
         accumulate_black(t.acc, p.nFrames);
         t.j = p.nFrames;
-        t.alive = false;
+        slot_retire(p, t, paths);
+        return;
     }
-    path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame); // the primary ray, traced once in the prologue
+    t.d0 = primary_direction(p.cam, x, y, p.width, p.height);
+    path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
+    t.alive = true;
+    t.fresh = true;
+    t.shadow = false;
 }
 
 // Start frame t.frame's path from the cached primary hit and run it up to its next trace:
-// on return the slot has a shadow or bounce ray in flight, or is retired. (Loops only when
-// paths end before any trace: no lights and roulette / bounce limit at the first bounce.)
+// on return the slot has a shadow or bounce ray in flight, or has retired its pixel. (Loops
+// only when paths end before any trace: no lights and roulette / bounce limit at bounce 0.)
 template <bool kChunked>
-__device__ __forceinline__ void slot_resume(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays)
+__device__ __forceinline__ void slot_resume(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays, uint32_t& paths)
 {
     const float4 sp = kChunked ? __ldg(p.spheres + t.cPrimary) : sphS[t.cPrimary];
     while (true)
     {
         if (t.j >= p.nFrames)
         {
-            t.alive = false;
+            slot_retire(p, t, paths);
             return;
         }
         path_begin(t.s, p.cam.pos, t.d0, t.pixel, t.frame);
@@ -509,26 +634,44 @@ __device__ __forceinline__ void slot_resume(const RenderParams& p, Slot& t, cons
 }
 
 template <bool kChunked>
-__device__ __forceinline__ void slot_finish(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays)
+__device__ __forceinline__ void slot_finish(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays, uint32_t& paths)
 {
     accumulate_sample(t.acc, t.s);
     t.j++;
     t.frame += p.frameStride;
-    slot_resume<kChunked>(p, t, sphS, rays);
+    slot_resume<kChunked>(p, t, sphS, rays, paths);
 }
 
 // the half-bounce that follows the trace of this slot's ray
 template <bool kChunked>
 __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, const float4* sphS, int closest, float tmin,
-                                             uint32_t& rays)
+                                             uint32_t& rays, uint32_t& paths)
 {
+    if (t.fresh)
+    {
+        // the primary ray of a newly claimed pixel: keep its hit for every frame
+        t.fresh = false;
+        t.tPrimary = tmin;
+        t.cPrimary = closest;
+        if (closest < 0)
+        {
+            accumulate_sky(p, t.acc, p.nFrames);
+            rays += p.nFrames;
+            t.j = p.nFrames;
+            slot_retire(p, t, paths);
+        }
+        else
+            slot_resume<kChunked>(p, t, sphS, rays, paths);
+        return;
+    }
+    rays++;
     bool bounce = false;
     if (!t.shadow)
     {
         if (closest < 0)
         {
             path_miss(p, t.s);
-            slot_finish<kChunked>(p, t, sphS, rays);
+            slot_finish<kChunked>(p, t, sphS, rays, paths);
             return;
         }
         const float4 sp = kChunked ? __ldg(p.spheres + closest) : sphS[closest];
@@ -544,7 +687,7 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
         bounce = true;
     }
     if (bounce && path_bounce(p, t.s))
-        slot_finish<kChunked>(p, t, sphS, rays);
+        slot_finish<kChunked>(p, t, sphS, rays, paths);
 }
 
 // one ray per slot against the whole scene
@@ -591,9 +734,7 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
     extern __shared__ float4 smem[];
     uint32_t* candS = reinterpret_cast<uint32_t*>(smem); // candWords x blockDim.x candidate words
     float4* sphS = smem + cand_words(p) * 256u / 4u;
-
-    uint32_t x, y;
-    thread_pixel_pair(x, y);
+    constexpr unsigned kFull = 0xffffffffu;
 
     if (!kChunked)
     {
@@ -602,81 +743,61 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
     }
 
     Slot a, b;
-    slot_init(p, a, x, y);
-    slot_init(p, b, x + 1u, y);
-    uint32_t rays = 0, traced = 0;
+    a.alive = b.alive = false;
+    a.fresh = b.fresh = false;
+    a.shadow = b.shadow = false;
+    a.j = b.j = 0;
+    a.pixel = b.pixel = 0;
+    a.acc = b.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    a.d0 = b.d0 = { 0.0f, 0.0f, 0.0f };
+    path_begin(a.s, p.cam.pos, a.d0, 0u, 0u);
+    path_begin(b.s, p.cam.pos, b.d0, 0u, 0u);
+    bool exhausted = false;
+    uint32_t rays = 0, traced = 0, paths = 0;
 
-    // ---- prologue: the primary rays, once per launch ----
-    if (kChunked ? __syncthreads_or(a.alive || b.alive) : (a.alive || b.alive))
+    while (true)
     {
-        float tmin0, tmin1;
-        int closest0, closest1;
-        trace_pair<kChunked>(p, sphS, candS, a, b, tmin0, closest0, tmin1, closest1);
-        if (a.alive)
+        // ---- claim pixels for idle slots ----
+        const bool needA = !a.alive && !exhausted, needB = !b.alive && !exhausted;
+        const uint32_t nNeed = __popc(__ballot_sync(kFull, needA)) + __popc(__ballot_sync(kFull, needB));
+        const bool anyAlive = __any_sync(kFull, a.alive || b.alive);
+        if (nNeed != 0u && (nNeed >= 2u * p.claimThreshold || !anyAlive))
         {
-            traced++;
-            a.tPrimary = tmin0;
-            a.cPrimary = closest0;
-            if (closest0 < 0)
-            {
-                accumulate_sky(p, a.acc, p.nFrames);
-                rays += p.nFrames;
-                a.j = p.nFrames;
-                a.alive = false;
-            }
-            else
-                slot_resume<kChunked>(p, a, sphS, rays);
+            const uint32_t idA = pool_claim(p.pool, needA);
+            if (needA)
+                slot_claim(p, a, idA, exhausted, paths);
+            const uint32_t idB = pool_claim(p.pool, needB && !exhausted);
+            if (needB && !exhausted)
+                slot_claim(p, b, idB, exhausted, paths);
         }
-        if (b.alive)
+        if (kChunked)
         {
-            traced++;
-            b.tPrimary = tmin1;
-            b.cPrimary = closest1;
-            if (closest1 < 0)
-            {
-                accumulate_sky(p, b.acc, p.nFrames);
-                rays += p.nFrames;
-                b.j = p.nFrames;
-                b.alive = false;
-            }
-            else
-                slot_resume<kChunked>(p, b, sphS, rays);
+            if (!__syncthreads_or(a.alive || b.alive || !exhausted))
+                break;
         }
-    }
+        else if (!__any_sync(kFull, a.alive || b.alive))
+        {
+            if (__all_sync(kFull, exhausted))
+                break;
+            continue;
+        }
 
-    while (kChunked ? __syncthreads_or(a.alive || b.alive) : (a.alive || b.alive))
-    {
         // ---- trace the ray in flight of each slot against every sphere (Renderer::traceRay) ----
         float tmin0, tmin1;
         int closest0, closest1;
         trace_pair<kChunked>(p, sphS, candS, a, b, tmin0, closest0, tmin1, closest1);
         if (a.alive)
         {
-            rays++;
             traced++;
-            slot_advance<kChunked>(p, a, sphS, closest0, tmin0, rays);
+            slot_advance<kChunked>(p, a, sphS, closest0, tmin0, rays, paths);
         }
         if (b.alive)
         {
-            rays++;
             traced++;
-            slot_advance<kChunked>(p, b, sphS, closest1, tmin1, rays);
+            slot_advance<kChunked>(p, b, sphS, closest1, tmin1, rays, paths);
         }
     }
-
-    if (a.inside)
-    {
-        p.accum[a.pixel] = a.acc;
-        if (p.emitRgba)
-            p.rgba[a.pixel] = pack_rgba8(a.acc, u32_to_f32_rn(p.rgbaDivisor));
-    }
-    if (b.inside)
-    {
-        p.accum[b.pixel] = b.acc;
-        if (p.emitRgba)
-            p.rgba[b.pixel] = pack_rgba8(b.acc, u32_to_f32_rn(p.rgbaDivisor));
-    }
-    count_rays(p, rays, traced, a.j + b.j);
+    count_rays(p, rays, traced, paths);
 }
 
 // ---------------------------------------------------------------------------
@@ -759,7 +880,10 @@ size_t megakernel_smem_bytes(const RenderParams& p)
 
 cudaError_t configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(megakernel_ww, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(megakernel_ww<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    e = cudaFuncSetAttribute(megakernel_ww<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
     e = cudaFuncSetAttribute(megakernel_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
@@ -768,15 +892,23 @@ cudaError_t configure()
     return cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
 }
 
-cudaError_t render_mega(const RenderParams& p, int kind, cudaStream_t s)
+cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream_t s)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
     const size_t smem = megakernel_smem_bytes(p);
+    // persistent CTAs: as many as stay resident (3 or 2 per SM), fewer for tiny images
+    const uint32_t byWork = (p.poolSize + 255u) / 256u;
     if (mega_kind(p, kind) == kMegaWhileWhile)
-        megakernel_ww<<<tile_grid(p.width, p.height), 256, smem, s>>>(p);
+    {
+        const uint32_t grid = min(static_cast<uint32_t>(smCount) * 3u, byWork);
+        if (p.nLights <= 1u)
+            megakernel_ww<true><<<grid, 256, smem, s>>>(p);
+        else
+            megakernel_ww<false><<<grid, 256, smem, s>>>(p);
+    }
     else
     {
-        const dim3 grid((p.width + 63u) / 64u, (p.height + 7u) / 8u);
+        const uint32_t grid = min(static_cast<uint32_t>(smCount) * 2u, (byWork + 1u) / 2u);
         if (chunked)
             megakernel_pair<true><<<grid, 256, smem, s>>>(p);
         else

@@ -27,7 +27,7 @@ int mega_kind(const atxk::RenderParams& p, int requested);
 cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, uint32_t nM, const float* lightAoS,
                        uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);
 size_t megakernel_smem_bytes(const atxk::RenderParams& p);
-cudaError_t render_mega(const atxk::RenderParams& p, int kind, cudaStream_t s);
+cudaError_t render_mega(const atxk::RenderParams& p, int kind, int smCount, cudaStream_t s);
 cudaError_t primary_hits(const atxk::RenderParams& p, int32_t* out, cudaStream_t s);
 cudaError_t ray_directions(const atxk::RenderParams& p, float* out, cudaStream_t s);
 cudaError_t resolve_rgba(const float4* accum, uint32_t* rgba, uint32_t n, uint32_t divisor, cudaStream_t s);

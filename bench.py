@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per step (default: the workload's)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference-CUDA legs")
     ap.add_argument("--mega-kind", type=int, default=0, help="0 auto, 1 while-while, 2 two-slot packed (same results)")
-    ap.add_argument("--trace-rounds", type=int, default=0, help="while-while form: closest-hit rounds per shading phase")
+    ap.add_argument("--park-threshold", type=int, default=0, help="while-while form: parked hits per warp that trigger the bounce phase")
+    ap.add_argument("--claim-threshold", type=int, default=0, help="idle lanes per warp that trigger a batched pixel claim")
     ap.add_argument("--chunk", type=int, default=0, help="force the shared-memory chunk size in spheres (0 = automatic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -218,10 +219,12 @@ def main():
     r = atx.Renderer(local_rank)
     r.setSettings(atx.Settings(True, False, bounces))
     r.setTuning(atx.TUNE_MEGA_KIND, args.mega_kind)
-    if args.trace_rounds:
-        r.setTuning(atx.TUNE_TRACE_ROUNDS, args.trace_rounds)
+    if args.park_threshold:
+        r.setTuning(atx.TUNE_PARK_THRESHOLD, args.park_threshold)
     if args.chunk:
         r.setTuning(atx.TUNE_CHUNK_SPHERES, args.chunk)
+    if args.claim_threshold:
+        r.setTuning(atx.TUNE_CLAIM_THRESHOLD, args.claim_threshold)
     r.onResize(W, H)
     cam.Resize(W, H)
     spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
@@ -329,7 +332,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
                        "spheres": int(len(spheres)), "lights": int(len(lights)), "parallelism": f"spp-split x{world}",
-                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel", "mega_kind": args.mega_kind, "trace_rounds": args.trace_rounds, "chunk": args.chunk},
+                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel", "mega_kind": args.mega_kind, "park_threshold": args.park_threshold, "chunk": args.chunk},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "grays_traced_per_s": rays_x / (total_ms * 1e-3) / 1e9,
             "wall_ms_total": wall_ms,

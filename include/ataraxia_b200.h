@@ -145,7 +145,10 @@ enum {
     ATX_TUNE_MEGA_KIND = 2,     /* megakernel form: 0 = by sphere count, 1 = while-while (one pixel
                                    per thread, hits gathered before the shading phase), 2 = two-slot
                                    packed (two pixels per thread, f32x2 sphere loop) */
-    ATX_TUNE_TRACE_ROUNDS = 3   /* while-while form: closest-hit rounds per shading phase (default 2) */
+    ATX_TUNE_PARK_THRESHOLD = 3 /* while-while form: parked hits per warp (1..32) that trigger the
+                                   bounce phase (default 8) */,
+    ATX_TUNE_CLAIM_THRESHOLD = 4 /* idle lanes per warp (1..32) that trigger a batched claim from the
+                                   pixel pool (default 8) */
 };
 ATX_API atx_status atx_set_tuning(atx_handle h, int key, int64_t value);
 

@@ -203,7 +203,7 @@ def test_chunked_staging_is_bit_identical(atx):
 
 
 def test_megakernel_forms_are_bit_identical(atx):
-    """while-while (1 pixel/thread) and two-slot packed (f32x2 sphere loop) forms, any trace-round count,
+    """while-while (1 pixel/thread) and two-slot packed (f32x2 sphere loop) forms, any park threshold,
     odd image sizes (partial tiles, an unpaired last column), sphere counts around the 8/32 block edges."""
     cases = [(atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 161, 91, 8, False, 5),
              (atx.synthetic.small(40, 3, seed=21), 192, 108, 6, True, 3),
@@ -213,9 +213,9 @@ def test_megakernel_forms_are_bit_identical(atx):
     for scene, W, H, bounces, sky, frames in cases:
         r, cam = setup(atx, scene, W, H, bounces, sky)
         ref = None
-        for kind, rounds in ((atx.MEGA_WHILE_WHILE, 1), (atx.MEGA_WHILE_WHILE, 2), (atx.MEGA_WHILE_WHILE, 5), (atx.MEGA_PAIR, 2)):
+        for kind, rounds in ((atx.MEGA_WHILE_WHILE, 1), (atx.MEGA_WHILE_WHILE, 12), (atx.MEGA_WHILE_WHILE, 32), (atx.MEGA_PAIR, 12)):
             r.setTuning(atx.TUNE_MEGA_KIND, kind)
-            r.setTuning(atx.TUNE_TRACE_ROUNDS, rounds)
+            r.setTuning(atx.TUNE_PARK_THRESHOLD, rounds)
             r.resetFrameIndex(); r.resetCounters()
             r.Render(cam, scene, frames=frames)
             acc, c = r.getAccumulation(), r.counters()
