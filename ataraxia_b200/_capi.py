@@ -17,7 +17,7 @@ SYMBOLS = [
     "atx_create", "atx_destroy", "atx_last_error", "atx_version",
     "atx_resize", "atx_upload_scene", "atx_set_camera", "atx_set_camera_matrices", "atx_set_settings",
     "atx_set_tuning", "atx_reset", "atx_frame_index",
-    "atx_render", "atx_render_frames", "atx_sync", "atx_last_render_ms", "atx_event_record", "atx_event_elapsed_ms",
+    "atx_render", "atx_render_frames", "atx_calibrate", "atx_sync", "atx_last_render_ms", "atx_event_record", "atx_event_elapsed_ms",
     "atx_read_accum", "atx_write_accum", "atx_read_rgba8", "atx_read_hit_ids", "atx_read_ray_directions",
     "atx_get_counters", "atx_reset_counters", "atx_accum_device_ptr", "atx_stream",
     "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum",
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         "atx_frame_index": [vp, C.POINTER(C.c_uint32)],
         "atx_render": [vp, C.c_uint32, C.c_int],
         "atx_render_frames": [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int],
+        "atx_calibrate": [vp, C.c_uint32, fp, fp],
         "atx_sync": [vp],
         "atx_last_render_ms": [vp, fp],
         "atx_event_record": [vp, C.c_int],

@@ -360,6 +360,13 @@ class Renderer:
     def renderFrames(self, first: int, count: int, stride: int = 1, zero_first: bool = False):
         check(_capi.lib().atx_render_frames(self._h, first, count, stride, int(zero_first), self.variant))
 
+    def calibrate(self, frames: int = 2):
+        """Time the megakernel and the wavefront variant on the current scene (scratch buffer) and make
+        VARIANT_AUTO the faster one. Returns (megakernel_ms, wavefront_ms)."""
+        a, b = C.c_float(), C.c_float()
+        check(_capi.lib().atx_calibrate(self._h, frames, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sync(self): check(_capi.lib().atx_sync(self._h))
 
     def lastRenderMs(self) -> float:

@@ -122,6 +122,9 @@ struct atx_renderer
     float* dRays = nullptr;
     unsigned long long* dCounters = nullptr;
     uint32_t* dPool = nullptr;  // pixel-pool counter of the persistent megakernels
+    void* dWave = nullptr;      // wavefront variant: path records, samples, queues (lazily allocated)
+    size_t waveBytes = 0;
+    int autoVariant = ATX_VARIANT_MEGAKERNEL; // what ATX_VARIANT_AUTO resolves to (atx_calibrate)
     int smCount = 0;
 
     // scene
@@ -266,7 +269,7 @@ atx_status atx_destroy(atx_handle h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && nccl().ok)
         nccl().CommDestroy(h->comm);
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool);
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
@@ -437,8 +440,8 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
 {
     if (variant != ATX_VARIANT_AUTO && variant != ATX_VARIANT_MEGAKERNEL && variant != ATX_VARIANT_WAVEFRONT)
         return fail(ATX_ERR_INVALID, "unknown variant %d", variant);
-    if (variant == ATX_VARIANT_WAVEFRONT)
-        return fail(ATX_ERR_INVALID, "the wavefront variant is not built in this version");
+    if (variant == ATX_VARIANT_AUTO)
+        variant = h->autoVariant;
     atxk::RenderParams p;
     if (atx_status s = make_params(h, p))
         return s;
@@ -448,6 +451,28 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.zeroFirst = zeroFirst ? 1 : 0;
     p.emitRgba = emitRgba ? 1 : 0;
     p.rgbaDivisor = rgbaDivisor;
+    if (variant == ATX_VARIANT_WAVEFRONT)
+    {
+        if (h->maxBounces > atx_launch::kWavefrontMaxBounces)
+            return fail(ATX_ERR_INVALID, "the wavefront variant supports maxBounces <= %d", atx_launch::kWavefrontMaxBounces);
+        if (static_cast<size_t>(h->nS) * sizeof(float4) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
+            return fail(ATX_ERR_INVALID, "the wavefront variant keeps the whole scene in shared memory: too many spheres");
+        const uint32_t P = h->width * h->height;
+        const uint32_t perWave = atx_launch::wavefront_frames_per_wave(P, n);
+        const size_t need = atx_launch::wavefront_bytes(perWave * P);
+        if (need > h->waveBytes)
+        {
+            ATX_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->dWave)
+                ATX_CUDA(cudaFree(h->dWave));
+            h->dWave = nullptr;
+            h->waveBytes = 0;
+            ATX_CUDA(cudaMalloc(&h->dWave, need));
+            h->waveBytes = need;
+        }
+        ATX_CUDA(atx_launch::render_wavefront(p, h->dWave, perWave, &h->launches, h->stream));
+        return ATX_OK;
+    }
     if (atx_launch::megakernel_smem_bytes(p) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
         return fail(ATX_ERR_INVALID, "shared-memory plan exceeds the device limit");
     // pixel claims: whole 8x4 tiles for the while-while form (its lockstep lives on coherent warps), small
@@ -511,6 +536,54 @@ atx_status atx_render_frames(atx_handle h, uint32_t first_frame, uint32_t n_fram
     }
     ATX_CUDA(cudaEventRecord(h->evStop, h->stream));
     h->timed = true;
+    return ATX_OK;
+}
+
+atx_status atx_calibrate(atx_handle h, uint32_t n_frames, float* megakernel_ms, float* wavefront_ms)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (n_frames == 0)
+        return fail(ATX_ERR_INVALID, "n_frames must be >= 1");
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    // render into a scratch buffer so the caller's accumulation is untouched
+    float4* keep = h->dAccum;
+    float4* scratch = nullptr;
+    const size_t bytes = static_cast<size_t>(h->width) * h->height * sizeof(float4);
+    ATX_CUDA(cudaMalloc(&scratch, bytes));
+    h->dAccum = scratch;
+    float ms[2] = { 0.0f, 0.0f };
+    const int variants[2] = { ATX_VARIANT_MEGAKERNEL, ATX_VARIANT_WAVEFRONT };
+    atx_status st = ATX_OK;
+    for (int v = 0; v < 2 && st == ATX_OK; v++)
+    {
+        for (int rep = 0; rep < 2 && st == ATX_OK; rep++) // first pass warms caches and allocations
+        {
+            cudaEventRecord(h->evStart, h->stream);
+            st = launch_frames(h, 1, n_frames, 1, true, variants[v], false, 1);
+            cudaEventRecord(h->evStop, h->stream);
+            if (st == ATX_OK && cudaEventSynchronize(h->evStop) != cudaSuccess)
+                st = fail(ATX_ERR_CUDA, "calibration launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (st == ATX_OK)
+                cudaEventElapsedTime(&ms[v], h->evStart, h->evStop);
+        }
+        if (st != ATX_OK && v == 1)
+        {
+            // the wavefront variant cannot run this configuration: the megakernel stays
+            ms[1] = -1.0f;
+            st = ATX_OK;
+        }
+    }
+    h->dAccum = keep;
+    cudaStreamSynchronize(h->stream);
+    cudaFree(scratch);
+    h->timed = false;
+    if (st != ATX_OK)
+        return st;
+    h->autoVariant = (ms[1] > 0.0f && ms[1] < ms[0]) ? ATX_VARIANT_WAVEFRONT : ATX_VARIANT_MEGAKERNEL;
+    if (megakernel_ms) *megakernel_ms = ms[0];
+    if (wavefront_ms) *wavefront_ms = ms[1];
     return ATX_OK;
 }
 

@@ -28,6 +28,11 @@ cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, ui
                        uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);
 size_t megakernel_smem_bytes(const atxk::RenderParams& p);
 cudaError_t render_mega(const atxk::RenderParams& p, int kind, int smCount, cudaStream_t s);
+// wavefront variant (atx_wavefront.cu)
+constexpr int kWavefrontMaxBounces = 254; // one queue counter per bounce
+size_t wavefront_bytes(uint32_t capacity);
+uint32_t wavefront_frames_per_wave(uint32_t pixels, uint32_t nFrames);
+cudaError_t render_wavefront(const atxk::RenderParams& p, void* work, uint32_t framesPerWave, uint64_t* launches, cudaStream_t s);
 cudaError_t primary_hits(const atxk::RenderParams& p, int32_t* out, cudaStream_t s);
 cudaError_t ray_directions(const atxk::RenderParams& p, float* out, cudaStream_t s);
 cudaError_t resolve_rgba(const float4* accum, uint32_t* rgba, uint32_t n, uint32_t divisor, cudaStream_t s);

@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per step (default: the workload's)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference-CUDA legs")
+    ap.add_argument("--variant", default="megakernel", choices=["megakernel", "wavefront", "auto"],
+                    help="kernel family (bit-identical results); auto = atx_calibrate's pick")
     ap.add_argument("--mega-kind", type=int, default=0, help="0 auto, 1 while-while, 2 two-slot packed (same results)")
     ap.add_argument("--park-threshold", type=int, default=0, help="while-while form: parked hits per warp that trigger the bounce phase")
     ap.add_argument("--claim-threshold", type=int, default=0, help="idle lanes per warp that trigger a batched pixel claim")
@@ -218,6 +220,7 @@ def main():
     cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
     r = atx.Renderer(local_rank)
     r.setSettings(atx.Settings(True, False, bounces))
+    r.variant = {"megakernel": atx.VARIANT_MEGAKERNEL, "wavefront": atx.VARIANT_WAVEFRONT, "auto": atx.VARIANT_AUTO}[args.variant]
     r.setTuning(atx.TUNE_MEGA_KIND, args.mega_kind)
     if args.park_threshold:
         r.setTuning(atx.TUNE_PARK_THRESHOLD, args.park_threshold)
@@ -251,6 +254,9 @@ def main():
             r.allreduceAccum()
         r.eventRecord(1)
 
+    calibration = None
+    if args.variant == "auto":
+        calibration = r.calibrate(2)
     for _ in range(args.warmup):
         step()
     r.sync()
@@ -332,7 +338,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
                        "spheres": int(len(spheres)), "lights": int(len(lights)), "parallelism": f"spp-split x{world}",
-                       "l2": "flushed between steps (256 MB write)", "variant": "megakernel", "mega_kind": args.mega_kind, "park_threshold": args.park_threshold, "chunk": args.chunk},
+                       "l2": "flushed between steps (256 MB write)", "variant": args.variant, "mega_kind": args.mega_kind, "park_threshold": args.park_threshold, "chunk": args.chunk},
+            "calibration_ms": calibration,
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "grays_traced_per_s": rays_x / (total_ms * 1e-3) / 1e9,
             "wall_ms_total": wall_ms,

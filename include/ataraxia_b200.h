@@ -82,9 +82,9 @@ typedef struct atx_counters {
 
 /* kernel family for atx_render* */
 enum {
-    ATX_VARIANT_AUTO = 0,      /* pick by measured divergence */
-    ATX_VARIANT_MEGAKERNEL = 1,/* one persistent path loop per pixel, path regeneration */
-    ATX_VARIANT_WAVEFRONT = 2  /* per-bounce queues with ray compaction */
+    ATX_VARIANT_AUTO = 0,      /* the faster of the two as measured by atx_calibrate */
+    ATX_VARIANT_MEGAKERNEL = 1,/* persistent path loops in registers, pixel pool, path regeneration */
+    ATX_VARIANT_WAVEFRONT = 2  /* path records in HBM, one launch per bounce, ray compaction */
 };
 
 typedef struct atx_renderer* atx_handle;
@@ -174,6 +174,15 @@ ATX_API atx_status atx_render(atx_handle h, uint32_t n_frames, int variant);
  * zero_first != 0 starts from a zeroed accumulation buffer. */
 ATX_API atx_status atx_render_frames(atx_handle h, uint32_t first_frame, uint32_t n_frames,
                                      uint32_t frame_stride, int zero_first, int variant);
+
+/* Decide what ATX_VARIANT_AUTO means for the current scene, camera, size and settings by
+ * measurement: renders n_frames frames with each variant into a scratch buffer (the
+ * accumulation buffer and frameIndex are untouched), times them with CUDA events and keeps
+ * the faster. The variants are bit-identical, so the choice never changes a result. The
+ * lane divergence of the megakernel against the HBM traffic of the wavefront queues is
+ * exactly what the two times weigh. Either output may be NULL; wavefront_ms is -1 when
+ * that variant cannot run the configuration. Without a calibration AUTO = megakernel. */
+ATX_API atx_status atx_calibrate(atx_handle h, uint32_t n_frames, float* megakernel_ms, float* wavefront_ms);
 
 /* Wait for everything queued on the handle's stream. */
 ATX_API atx_status atx_sync(atx_handle h);

@@ -227,6 +227,49 @@ def test_megakernel_forms_are_bit_identical(atx):
         r.close()
 
 
+def test_wavefront_variant_is_bit_identical(atx):
+    """Per-bounce launches with ray compaction (path records in HBM) against the megakernel: same bits,
+    same ray counts, several waves (frames > frames-per-wave), 0/1/many lights, sky on/off."""
+    cases = [(atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 161, 91, 8, False, 5),
+             (atx.synthetic.small(40, 3, seed=21), 192, 108, 6, True, 3),
+             (atx.synthetic.small(12, 0, seed=9), 64, 40, 4, True, 70),       # 70 frames > 64 per wave
+             (atx.synthetic.small(8, 1, seed=6), 64, 40, 0, False, 3)]        # maxBounces 0
+    for scene, W, H, bounces, sky, frames in cases:
+        r, cam = setup(atx, scene, W, H, bounces, sky)
+        r.Render(cam, scene, frames=frames)
+        ref, cref = r.getAccumulation(), r.counters()
+        img = r.getImage().data.copy()
+        r.variant = atx.VARIANT_WAVEFRONT
+        r.resetFrameIndex(); r.resetCounters()
+        r.Render(cam, scene, frames=frames)
+        c = r.counters()
+        assert (bits(r.getAccumulation()) == bits(ref)).all(), (W, H, bounces, frames)
+        assert (r.getImage().data == img).all()
+        assert c.paths == cref.paths and c.rays == cref.rays and c.rays_traced == c.rays
+        # split launches continue the same sums
+        r.resetFrameIndex()
+        r.Render(cam, scene, frames=1); r.Render(cam, scene, frames=frames - 1)
+        assert (bits(r.getAccumulation()) == bits(ref)).all()
+        r.close()
+
+
+def test_calibrate_picks_a_variant_without_touching_state(atx):
+    scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
+    r, cam = setup(atx, scene, 320, 180, 8, False)
+    r.Render(cam, scene, frames=4)
+    before, fi = r.getAccumulation(), r.frameIndex()
+    mega_ms, wave_ms = r.calibrate(2)
+    assert mega_ms > 0 and wave_ms > 0
+    assert (bits(r.getAccumulation()) == bits(before)).all() and r.frameIndex() == fi
+    r.variant = atx.VARIANT_AUTO
+    r.Render(cam, scene, frames=4)
+    auto = r.getAccumulation()
+    r.variant = atx.VARIANT_MEGAKERNEL
+    r.resetFrameIndex(); r.Render(cam, scene, frames=8)
+    assert (bits(r.getAccumulation()) == bits(auto)).all()
+    r.close()
+
+
 def test_split_launches_and_determinism(atx):
     scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
     r, cam = setup(atx, scene, 1920, 1080, 8, False)                # BASELINE config 2 geometry
