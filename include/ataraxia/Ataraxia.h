@@ -1,0 +1,580 @@
+// Ataraxia.h — header-only C++ mirror of the reference's host API for the path-tracing path
+// (Engine/include/{Scene,SceneNode,Camera,Renderer,Utils}.h of 1neskk/Ataraxia), over the C-ABI of
+// libataraxia_b200.so (include/ataraxia_b200.h). Same class names, method names, argument meaning
+// and error behaviour; no Vulkan, GLFW, ImGui, glm or CUDA headers needed by the caller.
+//
+//   reference                                        here
+//   glm::vec3 / quat / mat4                          atx::vec3 / quat / mat4 (layout-compatible, Math.h)
+//   Sphere, Material, Light, Settings, Ray           same PODs, same sizes (20 / 52 / 28 / 8 / 24 B)
+//   SceneNode (SceneNode.h:23-66, SceneNode.cpp)     same; transforms evaluated inside the library in glm's order
+//   Camera (Camera.h:14-88, Camera.cpp)              same minus onUpdate (GLFW input) and allocateDevice/freeDevice
+//                                                    (the ray table is never uploaded: rays are generated in-kernel)
+//   Image (Core/include/Image.h)                     headless: host RGBA8 pixels, getWidth/getHeight/setData
+//   Renderer (Renderer.h:19-31, Renderer.cu)         same + headless additions (frames per launch, accumulation
+//                                                    read-back, counters)
+//   Utils::importScene/exportScene/... (Utils.h)     same schema and file format (Json.h instead of nlohmann)
+//
+// All numerics that parity depends on (camera matrices, node transforms, sphere flattening) run inside
+// the library (atx_host_*), so the caller's compiler flags cannot perturb them.
+#pragma once
+
+#include "../ataraxia_b200.h"
+#include "Json.h"
+#include "Math.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace ataraxia
+{
+using atx::mat4;
+using atx::quat;
+using atx::vec2;
+using atx::vec3;
+using atx::vec4;
+
+// ---- PODs: Scene.h:11-56, SceneNode.h:11-21 -----------------------------------------------------
+struct Ray
+{
+    vec3 origin;
+    vec3 direction;
+};
+
+struct Light
+{
+    vec3 position;
+    vec3 color;
+    float intensity = 0.0f;
+    Light() = default;
+    Light(const vec3& pos, const vec3& col, float i) : position(pos), color(col), intensity(i) {}
+};
+
+struct Material
+{
+    vec3 albedo{ 1.0f };
+    float roughness = 0.0f;
+    float metallic = 0.0f;
+    vec3 F0{ 0.04f };
+    vec3 emissionColor{ 0.0f };
+    float emissionIntensity = 0.0f;
+    int id = 0;
+    vec3 getEmission() const { return emissionColor * emissionIntensity; }
+    Material() = default;
+    Material(const vec3& albedo_, float roughness_, float metallic_, const vec3& emissionColor_, float emissionIntensity_, int id_)
+        : albedo(albedo_), roughness(roughness_), metallic(metallic_), emissionColor(emissionColor_),
+          emissionIntensity(emissionIntensity_), id(id_) {}
+};
+
+struct Settings
+{
+    bool accumulation = true;
+    bool skyLight = false;
+    int maxBounces = 15;
+};
+
+struct Sphere
+{
+    vec3 center;
+    float radius = 0.0f;
+    int id = 0;
+    Sphere() = default;
+    Sphere(const vec3& c, float r, int materialId) : center(c), radius(r), id(materialId) {}
+};
+
+static_assert(sizeof(Sphere) == 20 && sizeof(Material) == 52 && sizeof(Light) == 28 && sizeof(Settings) == 8 && sizeof(Ray) == 24,
+              "POD layouts must match the reference (SURVEY.md §8c)");
+static_assert(sizeof(Sphere) == sizeof(atx_sphere) && sizeof(Material) == sizeof(atx_material) && sizeof(Light) == sizeof(atx_light),
+              "PODs are passed to the C-ABI as they are");
+
+// ---- SceneNode: SceneNode.h:23-66, SceneNode.cpp -------------------------------------------------
+class SceneNode
+{
+public:
+    SceneNode() : SceneNode("Untitled") {}                       // SceneNode.cpp:3-7
+    explicit SceneNode(const std::string& name)                  // SceneNode.cpp:9-13
+        : m_name(name), m_position(0.0f), m_rotation(), m_scale(1.0f), m_localTransform(1.0f), m_globalTransform(1.0f),
+          m_transformDirty(true) {}
+
+    void setPosition(const vec3& position) { m_position = position; m_transformDirty = true; }
+    void setRotation(const quat& rotation) { m_rotation = rotation; m_transformDirty = true; }
+    void setScale(const vec3& scale) { m_scale = scale; m_transformDirty = true; }
+    const vec3& getPosition() const { return m_position; }
+    const quat& getRotation() const { return m_rotation; }
+    const vec3& getScale() const { return m_scale; }
+
+    void addChild(std::shared_ptr<SceneNode> child) { m_children.push_back(std::move(child)); }            // :15-18
+    void removeChild(std::shared_ptr<SceneNode> child)                                                      // :20-28
+    {
+        m_children.erase(std::remove(m_children.begin(), m_children.end(), child), m_children.end());
+    }
+    const std::vector<std::shared_ptr<SceneNode>>& getChildren() const { return m_children; }
+
+    void addSphere(const Sphere& sphere) { m_spheres.push_back(sphere); }                                   // :30-33
+    void removeSphere(int sphereIndex)                                                                      // :35-40
+    {
+        if (sphereIndex >= 0 && sphereIndex < static_cast<int>(m_spheres.size()))
+            m_spheres.erase(m_spheres.begin() + sphereIndex);
+    }
+    const std::vector<Sphere>& getSpheres() const { return m_spheres; }
+
+    // SceneNode.cpp:42-59: local = T * R * S when dirty; global = parent * local; recurse
+    void updateGlobalTransform(const mat4& parentTransform = mat4(1.0f))
+    {
+        if (m_transformDirty)
+        {
+            const float rot[4] = { m_rotation.x, m_rotation.y, m_rotation.z, m_rotation.w };
+            atx_host_node_transform(&parentTransform[0].x, &m_position.x, rot, &m_scale.x, &m_localTransform[0].x,
+                                    &m_globalTransform[0].x);
+            m_transformDirty = false;
+        }
+        else
+            atx_host_mat4_mul(&parentTransform[0].x, &m_localTransform[0].x, &m_globalTransform[0].x);
+        for (auto& child : m_children)
+            child->updateGlobalTransform(m_globalTransform);
+    }
+    const mat4& getGlobalTransform() const { return m_globalTransform; }
+
+    const std::string& getName() const { return m_name; }
+    void setName(const std::string& name) { m_name = name; }
+
+private:
+    std::string m_name;
+    vec3 m_position;
+    quat m_rotation;
+    vec3 m_scale;
+    mat4 m_localTransform;
+    mat4 m_globalTransform;
+    std::vector<std::shared_ptr<SceneNode>> m_children;
+    std::vector<Sphere> m_spheres;
+    bool m_transformDirty;
+};
+
+// ---- Camera: Camera.h:14-88, Camera.cpp ----------------------------------------------------------
+class Camera
+{
+public:
+    Camera() = default;
+    // Camera.cpp:14-29: both value constructors preset 1600x900 and build view and projection
+    Camera(float fov, float nearClip, float farClip) : Camera(fov, nearClip, farClip, vec3(0.0f, 0.0f, 3.0f), vec3(0.0f, 0.0f, -1.0f)) {}
+    Camera(float fov, float nearClip, float farClip, vec3 position, vec3 direction)
+        : m_position(position), m_direction(direction), m_fov(fov), m_nearClip(nearClip), m_farClip(farClip), m_width(1600), m_height(900)
+    {
+        UpdateViewMatrix();
+        UpdateProjectionMatrix();
+    }
+
+    // Camera.cpp:110-127, including the early return that leaves a 1600x900 camera without a ray table (quirk Q-cam)
+    void Resize(uint32_t width, uint32_t height)
+    {
+        if (width == 0 || height == 0)
+        {
+            std::cerr << "Error: Width or height cannot be zero." << std::endl;
+            return;
+        }
+        if (width == m_width && height == m_height)
+            return;
+        m_width = width;
+        m_height = height;
+        m_projectionDirty = true;
+        UpdateProjectionMatrix();
+        m_rayDirection.clear(); // rebuilt on demand: the renderer generates rays in-kernel
+        m_raysValid = false;
+    }
+
+    const mat4& getViewMatrix() const { return m_viewMatrix; }
+    const mat4& getProjectionMatrix() const { return m_projectionMatrix; }
+    const mat4& getInverseViewMatrix() const { return m_inverseViewMatrix; }
+    const mat4& getInverseProjectionMatrix() const { return m_inverseProjectionMatrix; }
+    const vec3& getPosition() const { return m_position; }
+    const vec3& getDirection() const { return m_direction; }
+    const float& getFov() const { return m_fov; }
+    uint32_t getWidth() const { return m_width; }
+    uint32_t getHeight() const { return m_height; }
+
+    // the setters only mark dirty (Camera.h:56-58): matrices change on the next Update* call
+    void setPosition(const vec3& position) { m_position = position; m_viewDirty = true; }
+    void setDirection(const vec3& direction) { m_direction = direction; m_viewDirty = true; }
+    void setFov(float fov) { m_fov = fov; m_projectionDirty = true; }
+
+    // Camera::UpdateRayDirection (Camera.cpp:161-195): the host table, multithreaded like the reference
+    const std::vector<vec3>& getRayDirection() const
+    {
+        if (!m_raysValid && m_width && m_height)
+        {
+            m_rayDirection.resize(static_cast<size_t>(m_width) * m_height);
+            atx_host_ray_directions(&m_inverseProjectionMatrix[0].x, &m_inverseViewMatrix[0].x, m_width, m_height,
+                                    &m_rayDirection[0].x);
+            m_raysValid = true;
+        }
+        return m_rayDirection;
+    }
+    static float getRotationSpeed() { return 0.3f; }
+
+private:
+    void UpdateProjectionMatrix() // Camera.cpp:134-149
+    {
+        if (!m_projectionDirty)
+            return;
+        atx_host_camera_matrices(&m_position.x, &m_direction.x, m_fov, m_nearClip, m_farClip, std::max(m_width, 1u), std::max(m_height, 1u),
+                                 &m_projectionMatrix[0].x, nullptr, &m_inverseProjectionMatrix[0].x, nullptr);
+        m_projectionDirty = false;
+        m_raysValid = false;
+    }
+    void UpdateViewMatrix() // Camera.cpp:151-159
+    {
+        if (!m_viewDirty)
+            return;
+        atx_host_camera_matrices(&m_position.x, &m_direction.x, m_fov, m_nearClip, m_farClip, std::max(m_width, 1u), std::max(m_height, 1u),
+                                 nullptr, &m_viewMatrix[0].x, nullptr, &m_inverseViewMatrix[0].x);
+        m_viewDirty = false;
+        m_raysValid = false;
+    }
+
+    mat4 m_projectionMatrix{ 1.0f };
+    mat4 m_viewMatrix{ 1.0f };
+    mat4 m_inverseProjectionMatrix{ 1.0f };
+    mat4 m_inverseViewMatrix{ 1.0f };
+    vec3 m_position{ 0.0f };
+    vec3 m_direction{ 0.0f };
+    mutable std::vector<vec3> m_rayDirection;
+    mutable bool m_raysValid = false;
+    float m_fov = 45.0f;
+    float m_nearClip = 0.1f;
+    float m_farClip = 100.0f;
+    uint32_t m_width = 0, m_height = 0;
+    bool m_viewDirty = true;
+    bool m_projectionDirty = true;
+};
+
+// ---- Scene: Scene.h:58-80 ------------------------------------------------------------------------
+struct Scene
+{
+    std::shared_ptr<SceneNode> rootNode;
+    std::vector<Material> materials;
+    std::vector<Light> lights;
+    Settings settings;
+    Camera camera;
+    Scene() : rootNode(std::make_shared<SceneNode>("Scene")) {}
+};
+
+// ---- Image: the members Renderer touches (Core/include/Image.h; Renderer.cu:106, :121, :100, :242) ----
+enum class ImageType { None = 0, RGBA, RGBA32F };
+class Image
+{
+public:
+    Image(uint32_t width, uint32_t height, ImageType type = ImageType::RGBA, const void* data = nullptr)
+        : m_width(width), m_height(height), m_type(type), m_pixels(static_cast<size_t>(width) * height, 0u)
+    {
+        if (data)
+            setData(data);
+    }
+    void setData(const void* data) { std::memcpy(m_pixels.data(), data, m_pixels.size() * sizeof(uint32_t)); }
+    uint32_t getWidth() const { return m_width; }
+    uint32_t getHeight() const { return m_height; }
+    const uint32_t* getPixels() const { return m_pixels.data(); } // RGBA8, row 0 = bottom of the image (main.cpp:186-187 flips V)
+private:
+    uint32_t m_width, m_height;
+    ImageType m_type;
+    std::vector<uint32_t> m_pixels;
+};
+
+// ---- Renderer: Renderer.h:19-31, Renderer.cu ------------------------------------------------------
+class Renderer
+{
+public:
+    explicit Renderer(int device = 0)
+    {
+        if (atx_create(device, &m_handle) != ATX_OK)
+            report("atx_create");
+    }
+    ~Renderer()
+    {
+        atx_destroy(m_handle);
+        delete[] h_imageData_;
+    }
+    Renderer(const Renderer&) = delete; // the reference's shallow copy double-frees (DeviceMemory.h:33)
+    Renderer& operator=(const Renderer&) = delete;
+
+    // Renderer.cu:98-146
+    void onResize(uint32_t width, uint32_t height)
+    {
+        if (m_image && m_image->getWidth() == width && m_image->getHeight() == height)
+            return;
+        if (atx_resize(m_handle, width, height) != ATX_OK)
+        {
+            report("onResize");
+            return;
+        }
+        m_image = std::make_shared<Image>(width, height, ImageType::RGBA);
+        delete[] h_imageData_;
+        h_imageData_ = new uint32_t[static_cast<size_t>(width) * height];
+        m_width = width;
+        m_height = height;
+    }
+
+    // Renderer.cu:173-249. `frames` > 1 renders that many frames in ONE launch (bit-identical to that many calls).
+    void Render(Camera& camera, const Scene& scene, uint32_t frames = 1)
+    {
+        uint32_t frameIndex = 1;
+        atx_frame_index(m_handle, &frameIndex);
+        if (m_scene != &scene || frameIndex == 1) // :175-179
+        {
+            m_scene = &scene;
+            std::vector<Sphere> spheres;
+            traverseSceneGraph(scene.rootNode, mat4(1.0f), spheres);
+            for (const Sphere& s : spheres) // the message of Renderer.cu:32-36; the clamp itself happens in the library
+                if (static_cast<uint32_t>(s.id) >= scene.materials.size() && !scene.materials.empty())
+                    std::cerr << "Warning: Sphere has invalid material ID (" << s.id << "). Setting to 0." << std::endl;
+            if (atx_upload_scene(m_handle, reinterpret_cast<const atx_sphere*>(spheres.data()), spheres.size(),
+                                 reinterpret_cast<const atx_material*>(scene.materials.data()), scene.materials.size(),
+                                 reinterpret_cast<const atx_light*>(scene.lights.data()), scene.lights.size()) != ATX_OK)
+                return report("Render: scene upload");
+        }
+        if (!m_image)
+            return; // :184
+        if (atx_set_settings(m_handle, m_settings.accumulation, m_settings.skyLight, m_settings.maxBounces) != ATX_OK ||
+            atx_set_camera_matrices(m_handle, &camera.getPosition().x, &camera.getInverseProjectionMatrix()[0].x,
+                                    &camera.getInverseViewMatrix()[0].x) != ATX_OK)
+            return report("Render: state");
+        // a launch or execution error drops the frame and leaves frameIndex alone (Renderer.cu:226-238)
+        if (atx_render(m_handle, frames, m_variant) != ATX_OK || atx_read_rgba8(m_handle, h_imageData_, 0) != ATX_OK)
+            return report("Render");
+        m_image->setData(h_imageData_); // :242
+    }
+
+    std::shared_ptr<Image> getImage() const { return m_image; }
+    const Settings& getSettings() const { return m_settings; }
+    void setSettings(const Settings& settings) { m_settings = settings; }
+    void resetFrameIndex() { atx_reset(m_handle); }
+
+    // Renderer::traverseSceneGraph (Renderer.cu:67-96): pre-order; world-space centres, mean-scale radii
+    static void traverseSceneGraph(const std::shared_ptr<SceneNode>& node, const mat4& parentTransform, std::vector<Sphere>& spheres)
+    {
+        if (!node)
+            return;
+        node->updateGlobalTransform(parentTransform);
+        const mat4& g = node->getGlobalTransform();
+        for (const Sphere& s : node->getSpheres())
+        {
+            Sphere out;
+            atx_host_transform_sphere(&g[0].x, reinterpret_cast<const atx_sphere*>(&s), reinterpret_cast<atx_sphere*>(&out));
+            spheres.push_back(out);
+        }
+        for (const auto& child : node->getChildren())
+            traverseSceneGraph(child, g, spheres);
+    }
+
+    // ---- headless additions ----
+    atx_handle handle() const { return m_handle; }
+    void setVariant(int variant) { m_variant = variant; }
+    uint32_t frameIndex() const { uint32_t f = 1; atx_frame_index(m_handle, &f); return f; }
+    // float4 accumulation buffer (Renderer::d_accumulation_, Renderer.h:55): width*height*4 floats
+    std::vector<float> getAccumulation() const
+    {
+        std::vector<float> acc(static_cast<size_t>(m_width) * m_height * 4);
+        if (!acc.empty() && atx_read_accum(m_handle, acc.data()) != ATX_OK)
+            report("getAccumulation");
+        return acc;
+    }
+    std::vector<int32_t> getHitIds() const
+    {
+        std::vector<int32_t> hits(static_cast<size_t>(m_width) * m_height);
+        if (!hits.empty() && atx_read_hit_ids(m_handle, hits.data()) != ATX_OK)
+            report("getHitIds");
+        return hits;
+    }
+    atx_counters counters() const { atx_counters c{}; atx_get_counters(m_handle, &c); return c; }
+    float lastRenderMs() const { float ms = 0.0f; atx_last_render_ms(m_handle, &ms); return ms; }
+
+private:
+    static void report(const char* where) { std::cerr << "ataraxia_b200 (" << where << "): " << atx_last_error() << std::endl; }
+
+    atx_handle m_handle = nullptr;
+    std::shared_ptr<Image> m_image;
+    uint32_t* h_imageData_ = nullptr;
+    uint32_t m_width = 0, m_height = 0;
+    Settings m_settings;
+    const Scene* m_scene = nullptr;
+    int m_variant = ATX_VARIANT_AUTO;
+};
+
+// ---- Utils: Utils.h:11-23, Utils.cpp ---------------------------------------------------------------
+namespace Utils
+{
+using atx::Json;
+
+inline Json vec3ToJson(const vec3& v) { Json a = Json::array(); a.push_back(v.x); a.push_back(v.y); a.push_back(v.z); return a; }
+inline vec3 vec3FromJson(const Json& j) { return vec3(j[0].getFloat(), j[1].getFloat(), j[2].getFloat()); }
+
+inline Json serializeSceneNode(const std::shared_ptr<SceneNode>& node) // Utils.cpp:64-95
+{
+    Json j = Json::object();
+    j["name"] = node->getName();
+    Json t = Json::object();
+    t["position"] = vec3ToJson(node->getPosition());
+    const quat& q = node->getRotation();
+    Json r = Json::array();
+    r.push_back(q.x); r.push_back(q.y); r.push_back(q.z); r.push_back(q.w);
+    t["rotation"] = r;
+    t["scale"] = vec3ToJson(node->getScale());
+    j["transformation"] = t;
+    if (!node->getSpheres().empty())
+    {
+        Json spheres = Json::array();
+        for (const Sphere& s : node->getSpheres())
+        {
+            Json js = Json::object();
+            js["center"] = vec3ToJson(s.center);
+            js["radius"] = s.radius;
+            js["materialIndex"] = s.id;
+            spheres.push_back(js);
+        }
+        j["spheres"] = spheres;
+    }
+    if (!node->getChildren().empty())
+    {
+        Json children = Json::array();
+        for (const auto& c : node->getChildren())
+            children.push_back(serializeSceneNode(c));
+        j["children"] = children;
+    }
+    return j;
+}
+
+inline Json serializeScene(const Scene& scene) // Utils.cpp:3-51
+{
+    Json j = Json::object();
+    Json cam = Json::object();
+    cam["position"] = vec3ToJson(scene.camera.getPosition());
+    cam["direction"] = vec3ToJson(scene.camera.getDirection());
+    cam["fov"] = scene.camera.getFov();
+    j["camera"] = cam;
+    if (scene.rootNode)
+    {
+        scene.rootNode->updateGlobalTransform();
+        j["sceneGraph"] = serializeSceneNode(scene.rootNode);
+    }
+    if (!scene.materials.empty())
+    {
+        Json mats = Json::array();
+        for (const Material& m : scene.materials)
+        {
+            Json jm = Json::object();
+            jm["albedo"] = vec3ToJson(m.albedo);
+            jm["roughness"] = m.roughness;
+            jm["metallic"] = m.metallic;
+            jm["F0"] = vec3ToJson(m.F0);
+            jm["emissionIntensity"] = m.emissionIntensity;
+            jm["emissionColor"] = vec3ToJson(m.emissionColor);
+            mats.push_back(jm);
+        }
+        j["materials"] = mats;
+    }
+    if (!scene.lights.empty())
+    {
+        Json lights = Json::array();
+        for (const Light& l : scene.lights)
+        {
+            Json jl = Json::object();
+            jl["position"] = vec3ToJson(l.position);
+            jl["intensity"] = l.intensity;
+            jl["color"] = vec3ToJson(l.color);
+            lights.push_back(jl);
+        }
+        j["lights"] = lights;
+    }
+    Json s = Json::object();
+    s["maxBounces"] = scene.settings.maxBounces;
+    s["skyLight"] = scene.settings.skyLight;
+    s["accumulation"] = scene.settings.accumulation;
+    j["settings"] = s;
+    return j;
+}
+
+inline void exportScene(const Scene& scene, const std::string& filename) // Utils.cpp:53-62
+{
+    std::ofstream file(filename);
+    if (!file.is_open())
+    {
+        std::cerr << "Failed to open file for writing: " << filename << std::endl;
+        return;
+    }
+    file << serializeScene(scene).dump(4);
+}
+
+inline void deserializeSceneNode(const Json& j, std::shared_ptr<SceneNode>& node) // Utils.cpp:139-173
+{
+    if (!node) // an existing node (the scene root) keeps its own name
+        node = std::make_shared<SceneNode>(j["name"].getString());
+    const Json& t = j["transformation"];
+    node->setPosition(vec3FromJson(t["position"]));
+    const Json& r = t["rotation"]; // file order x, y, z, w; glm::quat(w, x, y, z) (Utils.cpp:145)
+    node->setRotation(quat(r[3].getFloat(), r[0].getFloat(), r[1].getFloat(), r[2].getFloat()));
+    node->setScale(vec3FromJson(t["scale"]));
+    if (j.contains("spheres"))
+        for (const Json& s : j["spheres"].items())
+            node->addSphere(Sphere(vec3FromJson(s["center"]), s["radius"].getFloat(), s["materialIndex"].getInt()));
+    if (j.contains("children"))
+        for (const Json& c : j["children"].items())
+        {
+            std::shared_ptr<SceneNode> child;
+            deserializeSceneNode(c, child);
+            node->addChild(child);
+        }
+}
+
+inline Scene deserializeScene(const Json& j) // Utils.cpp:97-137
+{
+    Scene scene; // default camera: setters only, no matrix update (quirk Q-cam ii)
+    scene.camera.setPosition(vec3FromJson(j["camera"]["position"]));
+    scene.camera.setDirection(vec3FromJson(j["camera"]["direction"]));
+    scene.camera.setFov(j["camera"]["fov"].getFloat());
+    if (j.contains("sceneGraph"))
+    {
+        deserializeSceneNode(j["sceneGraph"], scene.rootNode);
+        scene.rootNode->updateGlobalTransform();
+    }
+    for (const Json& m : j["materials"].items())
+    {
+        Material mat;
+        mat.albedo = vec3FromJson(m["albedo"]);
+        mat.roughness = m["roughness"].getFloat();
+        mat.metallic = m["metallic"].getFloat();
+        mat.F0 = vec3FromJson(m["F0"]);
+        mat.emissionIntensity = m["emissionIntensity"].getFloat();
+        mat.emissionColor = vec3FromJson(m["emissionColor"]);
+        scene.materials.push_back(mat); // Material::id is not serialised: stays 0
+    }
+    for (const Json& l : j["lights"].items())
+    {
+        Light light;
+        light.position = vec3FromJson(l["position"]);
+        light.intensity = l["intensity"].getFloat();
+        light.color = vec3FromJson(l["color"]);
+        scene.lights.push_back(light);
+    }
+    const Json& s = j["settings"];
+    scene.settings.maxBounces = s["maxBounces"].getInt();
+    scene.settings.skyLight = s["skyLight"].getBool();
+    scene.settings.accumulation = s["accumulation"].getBool();
+    return scene;
+}
+
+inline Scene importScene(const std::string& filename) // Utils.cpp:175-187: a missing file gives an empty Scene()
+{
+    std::ifstream file(filename);
+    if (!file.is_open())
+        return Scene();
+    std::stringstream ss;
+    ss << file.rdbuf();
+    return deserializeScene(Json::parse(ss.str()));
+}
+} // namespace Utils
+} // namespace ataraxia

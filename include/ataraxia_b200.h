@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary. The reference (1neskk/Ataraxia)
  * has no FFI layer: its boundary is the C++ class API in Engine/include. The
- * C++ mirror of that API (include/ataraxia/*.h: Renderer, Scene, SceneNode,
+ * C++ mirror of that API (include/ataraxia/Ataraxia.h: Renderer, Scene, SceneNode,
  * Camera, Material, Light, Settings, Utils) is a thin host layer over the
  * functions declared here, and every function cites the reference code it
  * replaces. Plain pointers and sizes only; no torch / glm / STL types.
@@ -244,7 +244,7 @@ ATX_API atx_status atx_allreduce_accum(atx_handle h);
  * CPU-side pieces of the reference's HOST API (they run on the CPU in the reference
  * too), compiled inside this library so the caller's compiler flags cannot perturb
  * the exact glm evaluation order parity depends on. Used by the header-only C++
- * mirror (include/ataraxia/*.h). None of them is on the render path. Matrices are
+ * mirror (include/ataraxia/Ataraxia.h). None of them is on the render path. Matrices are
  * column-major float[16] (glm::mat4 layout). */
 
 /* Camera::UpdateProjectionMatrix + UpdateViewMatrix, Camera.cpp:134-159. Any output

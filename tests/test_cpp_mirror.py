@@ -1,0 +1,112 @@
+"""The header-only C++ mirror of the reference API (include/ataraxia/Ataraxia.h) over the C-ABI:
+built with plain g++ (no nvcc, no glm, no nlohmann) and driven like reference user code.
+
+CPU part: scene.json import, scene-graph flatten, camera matrices and the host ray table are
+bit-identical to the Python mirror (which the other tests pin to the reference), and the C++ export is
+read back identically by the Python mirror and — where it was built — by the reference's own reader.
+GPU part (-m gpu): Renderer::Render through the C++ classes against the reference-CUDA golden vectors."""
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def driver(built, tmp_path_factory):
+    out = tmp_path_factory.mktemp("cpp") / "mirror_main"
+    lib = ROOT / "ataraxia_b200" / "lib"
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "cpp" / "mirror_main.cpp"),
+           "-o", str(out), f"-L{lib}", "-lataraxia_b200", f"-Wl,-rpath,{lib}"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return out
+
+
+def f32(x):
+    return np.asarray(x, np.float64).astype(np.float32)
+
+
+@pytest.mark.parametrize("file", ["sample_scene.json", "small_scene.json"])
+def test_cpp_host_side_matches_python_mirror(driver, built, tmp_path, file):
+    import ataraxia_b200 as atx
+    exported = tmp_path / "export.json"
+    proc = subprocess.run([str(driver), "cpu", str(GOLDEN / file), str(exported)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    got = json.loads(proc.stdout)
+    scene = atx.Utils.importScene(str(GOLDEN / file))
+    spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
+    assert len(got["spheres"]) == len(spheres)
+    g = np.array(got["spheres"], np.float64)
+    assert (f32(g[:, :3]).view(np.uint32) == spheres["center"].view(np.uint32)).all()
+    assert (f32(g[:, 3]).view(np.uint32) == spheres["radius"].view(np.uint32)).all()
+    assert (g[:, 4].astype(np.int32) == spheres["material"]).all()
+    assert got["materials"] == len(scene.materials) and got["lights"] == len(scene.lights)
+    assert got["maxBounces"] == scene.settings.maxBounces and got["rootName"] == "Scene"
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    cam.Resize(160, 90)
+    for key, m in (("projection", cam.getProjectionMatrix()), ("view", cam.getViewMatrix()),
+                   ("inverseProjection", cam.getInverseProjectionMatrix()), ("inverseView", cam.getInverseViewMatrix())):
+        assert (f32(got[key]).view(np.uint32) == np.asarray(m, np.float32).reshape(16).view(np.uint32)).all(), key
+    rays = cam.getRayDirection().reshape(-1, 3)
+    assert got["nRays"] == len(rays)
+    assert (f32(got["ray0"]).view(np.uint32) == rays[0].view(np.uint32)).all()
+    assert (f32(got["rayLast"]).view(np.uint32) == rays[-1].view(np.uint32)).all()
+    # the C++ export is the same scene for the Python reader
+    back = atx.Utils.importScene(str(exported))
+    s2 = atx.pack_spheres(atx.traverseSceneGraph(back.rootNode))
+    assert (s2.view(np.uint8) == spheres.view(np.uint8)).all()
+    assert (atx.pack_materials(back.materials).view(np.uint8) == atx.pack_materials(scene.materials).view(np.uint8)).all()
+    assert (atx.pack_lights(back.lights).view(np.uint8) == atx.pack_lights(scene.lights).view(np.uint8)).all()
+    assert json.loads(exported.read_text()) == atx.Utils.serializeScene(scene)
+
+
+def test_reference_reads_the_cpp_export(driver, refcpu, tmp_path):
+    """The reference's own Utils::importScene + traverseSceneGraph on a file written by the C++ mirror."""
+    import ataraxia_b200 as atx
+    exported = tmp_path / "export.json"
+    assert subprocess.run([str(driver), "cpu", str(GOLDEN / "small_scene.json"), str(exported)], capture_output=True).returncode == 0
+    scene = atx.Utils.importScene(str(GOLDEN / "small_scene.json"))
+    s, m, l, info = refcpu.load_scene(exported)
+    assert s.tobytes() == atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode)).tobytes()
+    assert m.tobytes() == atx.pack_materials(scene.materials).tobytes()
+    assert l.tobytes() == atx.pack_lights(scene.lights).tobytes()
+
+
+def test_cpp_missing_file_and_missing_key(driver, tmp_path):
+    # a missing file is an empty Scene (Utils.cpp:178-179): no spheres, no materials
+    proc = subprocess.run([str(driver), "cpu", str(tmp_path / "nope.json")], capture_output=True, text=True)
+    assert proc.returncode == 0 and '"spheres": []' in proc.stdout and '"materials": 0, "lights": 0, "maxBounces": 15' in proc.stdout
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"camera": {"position": [0,0,0], "direction": [0,0,-1]}}')   # no fov: nlohmann throws, so do we
+    proc = subprocess.run([str(driver), "cpu", str(bad)], capture_output=True, text=True)
+    assert proc.returncode != 0
+
+
+@pytest.mark.gpu
+def test_cpp_renderer_bit_exact_vs_reference_cuda_golden(driver, tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    gold = np.load(GOLDEN / "gpu_golden.npz")
+    for name, file in (("sample", "sample_scene.json"), ("small", "small_scene.json")):
+        W, H, bounces, sky, frames = (int(v) for v in gold[f"{name}_dims"])
+        out = tmp_path / f"{name}.bin"
+        proc = subprocess.run([str(driver), "gpu", str(GOLDEN / file), str(W), str(H), str(bounces), str(sky), str(frames), str(out)],
+                              capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stdout + proc.stderr
+        raw = np.fromfile(out, np.uint32)
+        P = W * H
+        hits = raw[:P].view(np.int32).reshape(H, W)
+        acc1 = raw[P:5 * P].reshape(H, W, 4)
+        accK = raw[5 * P:9 * P].reshape(H, W, 4)
+        rgba = raw[9 * P:10 * P].reshape(H, W)
+        assert (hits == gold[f"{name}_hits"]).all()
+        assert (acc1 == gold[f"{name}_acc1"].view(np.uint32)).all()
+        assert (accK == gold[f"{name}_accK"].view(np.uint32)).all()
+        assert (rgba == gold[f"{name}_rgbaK"]).all()
