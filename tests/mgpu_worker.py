@@ -1,0 +1,57 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (torchrun). Every rank renders its share of
+the frames into a zeroed buffer, the float4 buffers are summed with atx_allreduce_accum (NCCL over
+NVLink) and rank 0 compares with the same frames rendered sequentially on its own GPU."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import ataraxia_b200 as atx  # noqa: E402
+from ataraxia_b200.distributed import render_split  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    total, W, H, bounces = 2 * world + 3, 320, 180, 8
+    scene = atx.Utils.importScene(str(ROOT / "tests" / "golden" / "sample_scene.json"))
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    r = atx.Renderer(local)
+    r.setSettings(atx.Settings(True, False, bounces))
+    r.onResize(W, H); cam.Resize(W, H)
+    r.uploadScene(scene); r.setCamera(cam)
+    uid = [atx.Renderer.commUniqueId() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    r.commInitRank(world, rank, uid[0])
+    share = render_split(r, total, rank, world)          # frames rank+1, rank+1+world, ... then NCCL sum
+    reduced = r.getAccumulation()
+    rgba = r.getRGBA8(divisor=total)
+    ok = True
+    if rank == 0:
+        r.renderFrames(1, total, 1, zero_first=True)
+        seq = r.getAccumulation()
+        rgba_seq = r.getRGBA8(divisor=total)
+        ok &= bool((reduced[..., 3] == total).all())                                    # sample counts exact
+        ok &= bool(np.allclose(reduced[..., :3], seq[..., :3], rtol=2e-6, atol=1e-6))   # float reassociation only
+        d = np.abs(((rgba >> 8) & 0xFF).astype(int) - ((rgba_seq >> 8) & 0xFF).astype(int))
+        ok &= bool(d.max() <= 1)
+        print(f"MGPU world={world} total={total} share0={share.count} counts_ok={(reduced[..., 3] == total).all()} "
+              f"max_abs_diff={np.abs(reduced[..., :3] - seq[..., :3]).max():.3e} rgba_lsb={d.max()} ok={ok}", flush=True)
+    # every rank holds the same reduced buffer
+    t = torch.from_numpy(reduced.copy()).cuda()
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool((lo == hi).all().item())
+    r.commDestroy(); r.close()
+    dist.destroy_process_group()
+    sys.exit(0 if (ok and same) else 1)
+
+
+if __name__ == "__main__":
+    main()
