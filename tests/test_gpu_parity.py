@@ -289,6 +289,27 @@ def test_split_launches_and_determinism(atx):
     r.close()
 
 
+def test_config5_geometry_8k(atx):
+    """BASELINE config 5 geometry (7680x4320, sample scene, 8 bounces) at 2+1 spp: sample counts, split == one
+    launch, alpha, and the hit histogram in proportion to config 1's (same camera, 36x the pixels)."""
+    scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
+    r, cam = setup(atx, scene, 7680, 4320, 8, False)
+    r.Render(cam, scene, frames=3, readback=False)
+    one = r.getAccumulation()
+    assert (one[..., 3] == 3).all()
+    r.resetFrameIndex()
+    r.Render(cam, scene, frames=2, readback=False)
+    r.Render(cam, scene, frames=1, readback=False)
+    assert (bits(r.getAccumulation()) == bits(one)).all()
+    hits = r.getHitIds()
+    frac = np.array([(hits == k).mean() for k in (-1, 0, 1, 2)])
+    assert np.abs(frac - np.array([364231, 35974, 490333, 31062]) / 921600.0).max() < 2e-3
+    assert ((r.getRGBA8() >> 24) == 255).all()
+    c = r.counters()
+    assert c.paths == 2 * 7680 * 4320 * 3 and c.rays_traced <= c.rays
+    r.close()
+
+
 def test_spp_split_sums_to_sequential(atx):
     """Rank-style frame split (first, stride) into zeroed buffers, summed on the host."""
     from ataraxia_b200.distributed import frame_partition
