@@ -190,23 +190,23 @@ ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, fl
 //   cc  = fma(-r, r, q)                          2 scalar FFMA (FFMA2 has no negate modifier)
 //   m   = fma(cc, -a, 2^-100)                    FFMA2
 //   pre = fma(hb, hb, m)                         FFMA2
-//   rej = min(pre, -hb)                          2 FMNMX (ALU pipe)
-//   mask = (mask << 1) | signbit(rej)            2 SHF   (ALU pipe)
+//   mask = (mask << 1) | signbit(pre)            2 SHF   (ALU pipe)
 //
-// = 1 LDS.128 + 11 packed + 2 scalar FP + 4 ALU = 18 issue slots for two tests, while the
-// FMA pipe is busy 24 cycles: the loop is bound by the FP32 pipe (19 algorithmic flop per
-// 12 pipe-cycles -> 0.79 of peak at full lanes), not by the issue port.
+// = 1 LDS.128 + 11 packed + 2 scalar FP + 2 ALU = 16 instructions for two tests. A packed op
+// holds the issue port of its sub-partition for two cycles (tools/ubench_fp32.cu), so the group
+// costs 27 issue cycles per sphere for two rays in theory, 29.9 measured in isolation
+// (tools/ubench_filter.cu): 0.635 of FP32 peak is the ceiling of this loop (19 algorithmic
+// flop per 14.95 cycles x 2 flop/cycle/lane).
 //
-// A set sign bit proves the reference finds no hit on this sphere:
-//  * sign(pre): the line misses. hb and cc are bit-identical to the scalar sequence and
-//    pre >= fma(hb,hb,-(a*cc)); the +2^-100 only matters when |a*cc| < 2^-76, where it
-//    keeps the -0/flush cases of the reference's disc = fma(b,b,-(4a*cc)) on the
-//    candidate side. pre < 0 (not -0) implies disc < 0 (Renderer.cu:267).
-//  * sign(-hb), i.e. hb >= +0: then b = hb+hb >= 0 and t0 = (-b - sqrt(disc))/2a <= 0 or
-//    NaN, so min(t0,t1) fails "t > 0" (Renderer.cu:269-272): the sphere is behind the
-//    origin, or the origin sits on/inside it pointing away (the 1e-4 offset rays).
-// min() returns the other operand when one is NaN, which stays on the safe side: a NaN
-// pre defers to hb, a NaN hb (no hit possible) defers to pre.
+// A set sign bit proves the reference finds no hit on this sphere: the line misses it. hb and
+// cc are bit-identical to the scalar sequence and pre >= fma(hb,hb,-(a*cc)); the +2^-100 only
+// matters when |a*cc| < 2^-76, where it keeps the -0/flush cases of the reference's
+// disc = fma(b,b,-(4a*cc)) on the candidate side. pre < 0 (not -0) implies disc < 0
+// (Renderer.cu:267). A NaN pre has a clear sign bit (the device's canonical NaN), so it
+// stays a candidate.
+// (Also rejecting "hb >= 0" - sphere behind the origin - with min(pre, -hb) halves the
+// candidates but costs two more ALU instructions per sphere; measured 3 % slower at 4096
+// spheres, so it is not done.)
 // A clear bit makes the sphere a candidate; candidates are re-decided by exact_test in
 // ascending index order, so (tmin, closest) is exactly Renderer::traceRay's.
 // ---------------------------------------------------------------------------
@@ -228,13 +228,8 @@ ATX_DEV void filter_sphere(const float4 sp, const RayPair& r, uint32_t& m0, uint
     const float tiny = 7.888609052210118e-31f; // 2^-100
     const f32x2 m = ffma2(cc, r.na, pk2(tiny, tiny));
     const f32x2 pre = ffma2(hb, hb, m);
-#ifndef ATX_FILTER_NO_HB
-    m0 = shift_in_sign(m0, fmin_(lo2(pre), fneg(lo2(hb))));
-    m1 = shift_in_sign(m1, fmin_(hi2(pre), fneg(hi2(hb))));
-#else
     m0 = shift_in_sign(m0, lo2(pre));
     m1 = shift_in_sign(m1, hi2(pre));
-#endif
 }
 
 // Renderer::rayHit (Renderer.cu:396-409): p = (o - c) + d*t (fma); n = p * rsqrt(dot(p,p)); wp = p + c

@@ -87,6 +87,35 @@ __device__ __forceinline__ void stage_spheres(float4* dst, const float4* __restr
         dst[i] = i < count ? __ldg(src + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+// ---- bulk (TMA) staging of sphere chunks: cp.async.bulk global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+
+// one thread: expect `bytes` on the barrier, then start the copy (16 B aligned, multiple of 16 B)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "ATX_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra ATX_WAIT;\n"
+                 "}\n" ::"r"(smem_addr(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
 // scalar: one ray against spheres [0, count) resident at `sph`; indices offset by base
 __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, uint32_t base,
                                             float ox, float oy, float oz, float dx, float dy, float dz,
@@ -692,8 +721,8 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
 
 // one ray per slot against the whole scene
 template <bool kChunked>
-__device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* sphS, uint32_t* candS, const Slot& a,
-                                           const Slot& b, float& tmin0, int& closest0, float& tmin1, int& closest1)
+__device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* sphS, uint32_t* candS, uint64_t* mbar, uint32_t& phase,
+                                           const Slot& a, const Slot& b, float& tmin0, int& closest0, float& tmin1, int& closest1)
 {
     tmin0 = tmin1 = 3.402823466e+38f; // FLT_MAX
     closest0 = closest1 = -1;
@@ -709,22 +738,26 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
     }
     else
     {
-        // double-buffered chunk walk; all threads of the CTA take part in staging
+        // double-buffered chunk walk: one thread starts the bulk copy (TMA) of chunk c+1 while the CTA
+        // traces chunk c; the copy signals an mbarrier, the CTA barrier at the end of an iteration says
+        // "everyone is done with this buffer", which is what lets the next copy overwrite it
         const uint32_t C = p.chunkSpheres, stride = round_up8(C);
         const uint32_t nChunks = (p.nSpheres + C - 1) / C;
         float4* buf = const_cast<float4*>(sphS);
-        stage_spheres(buf, p.spheres, min(C, p.nSpheres));
+        if (threadIdx.x == 0)
+            bulk_load(buf, p.spheres, min(C, p.nSpheres) * 16u, &mbar[0]);
         for (uint32_t c = 0; c < nChunks; c++)
         {
-            __syncthreads(); // chunk c is resident
-            const float4* cur = buf + (c & 1u) * stride;
-            if (c + 1 < nChunks)
-                stage_spheres(buf + ((c + 1) & 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C));
+            const uint32_t cur = c & 1u;
+            if (c + 1 < nChunks && threadIdx.x == 0)
+                bulk_load(buf + (cur ^ 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C) * 16u, &mbar[cur ^ 1u]);
+            mbar_wait(&mbar[cur], (phase >> cur) & 1u); // chunk c has landed
+            phase ^= 1u << cur;
             if (a.alive || b.alive)
-                trace_range2(cur, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
+                trace_range2(buf + cur * stride, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
                              tmin0, closest0, tmin1, closest1);
+            __syncthreads();
         }
-        __syncthreads(); // nobody still reads the buffers when the next trace restages
     }
 }
 
@@ -732,15 +765,29 @@ template <bool kChunked>
 __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
 {
     extern __shared__ float4 smem[];
-    uint32_t* candS = reinterpret_cast<uint32_t*>(smem); // candWords x blockDim.x candidate words
-    float4* sphS = smem + cand_words(p) * 256u / 4u;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);        // kChunked: one mbarrier per staging buffer
+    uint32_t* candS = reinterpret_cast<uint32_t*>(smem + 1);   // candWords x blockDim.x candidate words
+    float4* sphS = smem + 1 + cand_words(p) * 256u / 4u;
     constexpr unsigned kFull = 0xffffffffu;
+    uint32_t phase = 0u; // parity of the next completion of each mbarrier
 
     if (!kChunked)
-    {
         stage_spheres(sphS, p.spheres, p.nSpheres);
-        __syncthreads();
+    else
+    {
+        // the padded tail of a buffer is masked out of the candidate set, never tested; zero it once so
+        // no uninitialised shared memory is ever read
+        const uint32_t words = 2u * round_up8(p.chunkSpheres);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+            sphS[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&mbar[0], 1u);
+            mbar_init(&mbar[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
+    __syncthreads();
 
     Slot a, b;
     a.alive = b.alive = false;
@@ -785,7 +832,7 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
         // ---- trace the ray in flight of each slot against every sphere (Renderer::traceRay) ----
         float tmin0, tmin1;
         int closest0, closest1;
-        trace_pair<kChunked>(p, sphS, candS, a, b, tmin0, closest0, tmin1, closest1);
+        trace_pair<kChunked>(p, sphS, candS, mbar, phase, a, b, tmin0, closest0, tmin1, closest1);
         if (a.alive)
         {
             traced++;
@@ -875,7 +922,7 @@ size_t megakernel_smem_bytes(const RenderParams& p)
     const bool chunked = p.chunkSpheres < p.nSpheres;
     const size_t pad8 = (static_cast<size_t>(chunked ? p.chunkSpheres : p.nSpheres) + 7u) & ~size_t(7);
     // the two-slot form also keeps cand_words() candidate words per thread (sized for both forms)
-    return sizeof(float4) * (chunked ? 2 * pad8 : pad8) + sizeof(uint32_t) * cand_words(p) * 256u;
+    return sizeof(float4) * (1 + (chunked ? 2 * pad8 : pad8)) + sizeof(uint32_t) * cand_words(p) * 256u; // +16 B: two mbarriers
 }
 
 cudaError_t configure()

@@ -99,6 +99,11 @@ def config4() -> Scene:
     return make_scene(4096, 4, (-60.0, 0.3, -60.0), (60.0, 20.0, 60.0), 0.2, 0.8, (0.0, 25.0, 110.0), (0.0, -0.15, -1.0))
 
 
+def stress16k() -> Scene:
+    """16384 spheres (beyond the resident shared-memory budget: the chunked, TMA-staged walk), same box as config 4."""
+    return make_scene(16384, 4, (-60.0, 0.3, -60.0), (60.0, 20.0, 60.0), 0.15, 0.5, (0.0, 25.0, 110.0), (0.0, -0.15, -1.0))
+
+
 def small(n_spheres=24, n_lights=3, seed=7) -> Scene:
     """Small mixed scene for fast parity tests (emissive + metallic + diffuse, several lights)."""
     return make_scene(n_spheres, n_lights, (-4.0, 0.3, -4.0), (4.0, 3.0, 4.0), 0.3, 0.9, (0.0, 3.0, 12.0),

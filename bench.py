@@ -44,12 +44,15 @@ WORKLOADS = {
     "c3": ("synthetic 256 spheres 16 lights 3840x2160 256spp 8 bounces", 3840, 2160, 256, 8),
     "c4": ("synthetic 4096 spheres 3840x2160 64spp 8 bounces", 3840, 2160, 64, 8),
     "c1": ("sample-scene-data/scene.json 1280x720 1spp 5 bounces", 1280, 720, 1, 5),
+    "c16k": ("synthetic 16384 spheres (chunked TMA staging) 1920x1080 16spp 8 bounces", 1920, 1080, 16, 8),
 }
 
 
 def load_scene(atx, name):
     if name in ("c1", "c2"):
         return atx.Utils.importScene(str(ROOT / "tests" / "golden" / "sample_scene.json"))
+    if name == "c16k":
+        return atx.synthetic.stress16k()
     return atx.synthetic.config3() if name == "c3" else atx.synthetic.config4()
 
 
