@@ -176,7 +176,10 @@ ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, fl
     const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
     const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
     const float pre = ffma(hb, hb, fneg(fmul(k.a, cc)));
-    if (!(pre < 0.0f))
+    // hb >= 0 (or NaN): b = hb+hb >= 0, so t0 = (-b - sqrt(disc))/2a <= 0 or NaN and min(t0,t1) fails "t > 0"
+    // (Renderer.cu:269-272): the sphere is behind the origin, or the origin sits on it pointing away (the
+    // 1e-4 offset rays leaving a surface) - no hit either way, so the literal sequence is skipped
+    if (!(pre < 0.0f) && hb < 0.0f)
         exact_tail(hb, cc, index, k, tmin, closest);
 }
 
@@ -305,7 +308,7 @@ ATX_DEV V3 cook_torrance(const float4 m0, const float4 m1, const float4 m2, cons
 // Tangent frame + combination shared by both samplers (BRDF.cu:83-92 / :107-116):
 // T from the larger of |N.x|,|N.y|; B = cross(N,T) (fma(a,b,-(c*d)) as ptxas contracts it); result = x*T + y*B + z*N
 // as fma(z, N, fma(x, T, y*B)).
-ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
+ATX_DEV void tangent_frame(const V3 N, V3& T, V3& B)
 {
     // the two branches of the reference differ only in which component of N pairs with N.z;
     // selecting the operands instead of branching runs the same instructions on the same values
@@ -313,16 +316,28 @@ ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
     const float major = xMajor ? N.x : N.y;
     const float s = fsqrt_approx(ffma(N.z, N.z, fmul(major, major)));
     const float nz = fneg(N.z);
-    const float Tx = fdiv_approx(xMajor ? nz : 0.0f, s);
-    const float Ty = fdiv_approx(xMajor ? 0.0f : nz, s);
-    const float Tz = fdiv_approx(major, s);
+    T.x = fdiv_approx(xMajor ? nz : 0.0f, s);
+    T.y = fdiv_approx(xMajor ? 0.0f : nz, s);
+    T.z = fdiv_approx(major, s);
     // cross(N, T): ptxas fuses the first product of each component (sampler SASS 0x380-0x3d0)
-    const float Bx = ffma(N.y, Tz, fneg(fmul(Ty, N.z)));
-    const float By = ffma(Tx, N.z, fneg(fmul(N.x, Tz)));
-    const float Bz = ffma(N.x, Ty, fneg(fmul(N.y, Tx)));
-    return { ffma(z, N.x, ffma(x, Tx, fmul(y, Bx))),
-             ffma(z, N.y, ffma(x, Ty, fmul(y, By))),
-             ffma(z, N.z, ffma(x, Tz, fmul(y, Bz))) };
+    B.x = ffma(N.y, T.z, fneg(fmul(T.y, N.z)));
+    B.y = ffma(T.x, N.z, fneg(fmul(N.x, T.z)));
+    B.z = ffma(N.x, T.y, fneg(fmul(N.y, T.x)));
+}
+
+// result = x*T + y*B + z*N as fma(z, N, fma(x, T, y*B))
+ATX_DEV V3 frame_combine(const V3 N, const V3 T, const V3 B, float x, float y, float z)
+{
+    return { ffma(z, N.x, ffma(x, T.x, fmul(y, B.x))),
+             ffma(z, N.y, ffma(x, T.y, fmul(y, B.y))),
+             ffma(z, N.z, ffma(x, T.z, fmul(y, B.z))) };
+}
+
+ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
+{
+    V3 T, B;
+    tangent_frame(N, T, B);
+    return frame_combine(N, T, B, x, y, z);
 }
 
 // BRDF::sampleHemisphereCosineWeighted (BRDF.cu:72-93) and BRDF::sampleGGX (BRDF.cu:95-117) in one
@@ -332,12 +347,12 @@ ATX_DEV V3 to_world(const V3 N, float x, float y, float z)
 //   GGX   : z = sqrt((1 - u1) / fma(ggxT, u1, 1)), r = sqrt(fma(-z, z, 1)), ggxT = fma(a, a, -1), a = roughness^2
 //           (1 - cos^2 is contracted by ptxas, sampler SASS 0x2d0). The half-vector itself is returned as
 //           the new direction (reference quirk Q-ggx).
-ATX_DEV V3 sample_direction(const V3 N, bool ggx, float ggxT, uint32_t& seed)
+ATX_DEV void sample_local(bool ggx, float ggxT, uint32_t& seed, float& x, float& y, float& z)
 {
     const float u1 = pcg_float(seed);
     const float u2 = pcg_float(seed);
     const float omu = fsub(1.0f, u1);
-    float r, z;
+    float r;
     if (ggx)
     {
         z = fsqrt_approx(fdiv_approx(omu, ffma(ggxT, u1, 1.0f)));
@@ -349,8 +364,14 @@ ATX_DEV V3 sample_direction(const V3 N, bool ggx, float ggxT, uint32_t& seed)
         z = fsqrt_approx(omu);
     }
     const float phi = fmul(u2, 6.28318548f);
-    const float x = fmul(r, fcos_approx(phi));
-    const float y = fmul(r, fsin_approx(phi));
+    x = fmul(r, fcos_approx(phi));
+    y = fmul(r, fsin_approx(phi));
+}
+
+ATX_DEV V3 sample_direction(const V3 N, bool ggx, float ggxT, uint32_t& seed)
+{
+    float x, y, z;
+    sample_local(ggx, ggxT, seed, x, y, z);
     return to_world(N, x, y, z);
 }
 

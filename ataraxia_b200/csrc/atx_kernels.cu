@@ -374,10 +374,15 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
     float tminP = 0.0f, tPrimary = 0.0f;
     int closestP = -1, cPrimary = -1;
     uint32_t raysPerStart = 1; // reference traceRay calls a cached start stands for
-    // kFixedLight: path state after the first bounce's shading
+    // kFixedLight: what every frame of this pixel shares - the path state after the first bounce's shading
+    // (color, next origin, normal, material) and the frame-independent half of the first path_bounce:
+    // throughput = 1 * albedo, so the roulette probability pr0, the throughput after it (tq) and the
+    // tangent frame of N are per-pixel constants; each frame only draws its three random numbers
     float c0r = 0.0f, c0g = 0.0f, c0b = 0.0f, o0x = 0.0f, o0y = 0.0f, o0z = 0.0f;
-    V3 N0 = { 0.0f, 0.0f, 0.0f };
+    V3 N0 = { 0.0f, 0.0f, 0.0f }, T0 = { 0.0f, 0.0f, 0.0f }, B0 = { 0.0f, 0.0f, 0.0f };
+    float pr0 = 0.0f, tq0x = 0.0f, tq0y = 0.0f, tq0z = 0.0f, ggxT0 = 0.0f;
     int mat0 = 0;
+    bool ggx0 = false;
     uint32_t rays = 0, traced = 0, paths = 0;
 
     auto trace = [&](float& tmin, int& closest) {
@@ -416,16 +421,28 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
                 closestP = cPrimary;
                 return;
             }
+            // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in
             s.cr = c0r; s.cg = c0g; s.cb = c0b;
-            s.ox = o0x; s.oy = o0y; s.oz = o0z;
-            s.N = N0;
-            s.matIndex = mat0;
-            s.tx = s.ty = s.tz = 1.0f;
             s.seed = pixel * frame;
-            s.bounce = 0;
             parked = false;
-            if (!path_bounce(p, s))
-                return;
+            if (!(pcg_float(s.seed) > pr0))
+            {
+                float x, y, z;
+                sample_local(ggx0, ggxT0, s.seed, x, y, z);
+                const V3 nd = frame_combine(N0, T0, B0, x, y, z);
+                if (1 < p.maxBounces)
+                {
+                    s.ox = o0x; s.oy = o0y; s.oz = o0z;
+                    s.dx = nd.x; s.dy = nd.y; s.dz = nd.z;
+                    s.tx = tq0x; s.ty = tq0y; s.tz = tq0z;
+                    s.N = N0;
+                    s.matIndex = mat0;
+                    s.bounce = 1;
+                    s.seed += 1u; // Renderer.cu:306
+                    return;
+                }
+            }
+            // the path ended at its first roulette or at the bounce limit: the sample is the cached color
             accumulate_sample(acc, s);
             j++;
             frame += p.frameStride;
@@ -523,6 +540,18 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
                     o0x = s.ox; o0y = s.oy; o0z = s.oz;
                     N0 = s.N;
                     mat0 = s.matIndex;
+                    {
+                        // the same instructions path_bounce runs, on the values every frame would feed it
+                        const float4 m0 = __ldg(p.mats + kMatStride * mat0 + 0);
+                        const float4 m1 = __ldg(p.mats + kMatStride * mat0 + 1);
+                        const float ax = fmul(1.0f, m0.x), ay = fmul(1.0f, m0.y), az = fmul(1.0f, m0.z);
+                        const float len = fsqrt_approx(fdot3(ax, ay, az, ax, ay, az));
+                        pr0 = fmax_(fmin_(len, 1.0f), 0.1f);
+                        tq0x = fdiv_approx(ax, pr0); tq0y = fdiv_approx(ay, pr0); tq0z = fdiv_approx(az, pr0);
+                        ggx0 = m1.w > 0.0f;
+                        ggxT0 = ggx0 ? __ldg(p.mats + kMatStride * mat0 + 5).x : 0.0f;
+                        tangent_frame(N0, T0, B0);
+                    }
                     fresh = false;
                     start();
                 }
