@@ -288,26 +288,39 @@ __device__ __forceinline__ void count_rays(const RenderParams& p, uint32_t rays,
     }
 }
 
-// perPixel's loop does not run when maxBounces < 1: every sample is (0,0,0,1)   (Renderer.cu:303-304, :386)
-__device__ __forceinline__ void accumulate_black(float4& acc, uint32_t n)
+// n samples of the same color c added one by one: accumulation[p] += vec4(c, 1)  (Renderer.cu:165, :386).
+// When c is exactly (0,0,0) the loop has a closed form that is bit-identical: x + 0 is x after the first
+// addition (which also turns a -0 into +0), and the count stays an exactly representable integer while
+// it is below 2^24, so w + 1 + ... + 1 == w + n.
+__device__ __forceinline__ void accumulate_constant(float4& acc, float cr, float cg, float cb, uint32_t n)
 {
+    const bool zero = cr == 0.0f && cg == 0.0f && cb == 0.0f;
+    const float w = acc.w;
+    if (zero && n > 0u && w >= 0.0f && w == floorf(w) && w + static_cast<float>(n) <= 16777216.0f && n <= 16777216u)
+    {
+        acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
+        acc.w = w + static_cast<float>(n);
+        return;
+    }
     for (uint32_t q = 0; q < n; q++)
     {
-        acc.x = fadd(0.0f, acc.x); acc.y = fadd(0.0f, acc.y); acc.z = fadd(0.0f, acc.z);
+        acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
         acc.w = fadd(acc.w, 1.0f);
     }
 }
 
+// perPixel's loop does not run when maxBounces < 1: every sample is (0,0,0,1)   (Renderer.cu:303-304, :386)
+__device__ __forceinline__ void accumulate_black(float4& acc, uint32_t n) { accumulate_constant(acc, 0.0f, 0.0f, 0.0f, n); }
+
 // A pixel whose primary ray misses every sphere: each frame's path is "miss at bounce 0"
-// (Renderer.cu:309-318 with throughput 1), so all its samples are added in one short loop.
+// (Renderer.cu:309-318 with throughput 1), so all its samples are the same color.
 __device__ __forceinline__ void accumulate_sky(const RenderParams& p, float4& acc, uint32_t n)
 {
     PathState s;
     s.cr = s.cg = s.cb = 0.0f;
     s.tx = s.ty = s.tz = 1.0f;
     path_miss(p, s);
-    for (uint32_t q = 0; q < n; q++)
-        accumulate_sample(acc, s);
+    accumulate_constant(acc, s.cr, s.cg, s.cb, n);
 }
 
 // ---------------------------------------------------------------------------
