@@ -232,6 +232,15 @@ class Image:
     def getHeight(self): return self.m_height
     def setData(self, data): self.data = data
 
+    def savePPM(self, path: str) -> None:
+        """Output sink in place of the Vulkan texture upload (Core/src/Image.cpp:183-271): binary PPM, rows top to
+        bottom, i.e. with the V flip the UI applies when it shows the texture (main.cpp:185-187)."""
+        px = np.ascontiguousarray(self.data[::-1])
+        rgb = np.stack([px & 0xFF, (px >> 8) & 0xFF, (px >> 16) & 0xFF], axis=-1).astype(np.uint8)
+        with open(path, "wb") as f:
+            f.write(f"P6\n{self.m_width} {self.m_height}\n255\n".encode())
+            f.write(rgb.tobytes())
+
 
 def traverseSceneGraph(node: Optional[SceneNode], parentTransform=None) -> List[Sphere]:
     """Renderer::traverseSceneGraph (Renderer.cu:67-96): pre-order, world-space centres, mean-scale radii."""

@@ -279,6 +279,29 @@ public:
     uint32_t getWidth() const { return m_width; }
     uint32_t getHeight() const { return m_height; }
     const uint32_t* getPixels() const { return m_pixels.data(); } // RGBA8, row 0 = bottom of the image (main.cpp:186-187 flips V)
+
+    // Output sink that replaces the Vulkan texture upload (Core/src/Image.cpp:183-271): binary PPM (P6), rows
+    // written top to bottom, i.e. with the V flip the UI applies when it shows the texture (main.cpp:185-187).
+    bool savePPM(const std::string& path) const
+    {
+        std::ofstream f(path, std::ios::binary);
+        if (!f.is_open())
+            return false;
+        f << "P6\n" << m_width << " " << m_height << "\n255\n";
+        std::vector<unsigned char> row(static_cast<size_t>(m_width) * 3);
+        for (uint32_t y = 0; y < m_height; y++)
+        {
+            const uint32_t* src = m_pixels.data() + static_cast<size_t>(m_height - 1 - y) * m_width;
+            for (uint32_t x = 0; x < m_width; x++)
+            {
+                row[3 * x + 0] = static_cast<unsigned char>(src[x] & 0xFFu);         // vec4ToRGBA: r in the low byte (Renderer.h:70-78)
+                row[3 * x + 1] = static_cast<unsigned char>((src[x] >> 8) & 0xFFu);
+                row[3 * x + 2] = static_cast<unsigned char>((src[x] >> 16) & 0xFFu);
+            }
+            f.write(reinterpret_cast<const char*>(row.data()), static_cast<std::streamsize>(row.size()));
+        }
+        return f.good();
+    }
 private:
     uint32_t m_width, m_height;
     ImageType m_type;
@@ -391,6 +414,27 @@ public:
         return hits;
     }
     atx_counters counters() const { atx_counters c{}; atx_get_counters(m_handle, &c); return c; }
+    // float radiance (accumulation / samples, unclamped) as a little-endian PFM, bottom row first as PFM defines it
+    bool saveAccumulationPFM(const std::string& path) const
+    {
+        const std::vector<float> acc = getAccumulation();
+        std::ofstream f(path, std::ios::binary);
+        if (!f.is_open() || acc.empty())
+            return false;
+        f << "PF\n" << m_width << " " << m_height << "\n-1.0\n";
+        std::vector<float> row(static_cast<size_t>(m_width) * 3);
+        for (uint32_t y = 0; y < m_height; y++)
+        {
+            for (uint32_t x = 0; x < m_width; x++)
+            {
+                const float* a = &acc[(static_cast<size_t>(y) * m_width + x) * 4];
+                const float n = a[3] > 0.0f ? a[3] : 1.0f;
+                row[3 * x + 0] = a[0] / n; row[3 * x + 1] = a[1] / n; row[3 * x + 2] = a[2] / n;
+            }
+            f.write(reinterpret_cast<const char*>(row.data()), static_cast<std::streamsize>(row.size() * sizeof(float)));
+        }
+        return f.good();
+    }
     float lastRenderMs() const { float ms = 0.0f; atx_last_render_ms(m_handle, &ms); return ms; }
 
 private:

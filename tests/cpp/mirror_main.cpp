@@ -72,6 +72,11 @@ int main(int argc, char** argv)
         std::fwrite(accK.data(), sizeof(float), accK.size(), f);
         std::fwrite(renderer.getImage()->getPixels(), sizeof(uint32_t), static_cast<size_t>(W) * H, f);
         std::fclose(f);
+        if (argc > 9)
+        {
+            renderer.getImage()->savePPM(std::string(argv[9]) + ".ppm");
+            renderer.saveAccumulationPFM(std::string(argv[9]) + ".pfm");
+        }
         std::printf("frameIndex %u paths %llu\n", renderer.frameIndex(), static_cast<unsigned long long>(renderer.counters().paths));
         return renderer.frameIndex() == static_cast<uint32_t>(frames) + 1 ? 0 : 4;
     }

@@ -97,8 +97,8 @@ def test_cpp_renderer_bit_exact_vs_reference_cuda_golden(driver, tmp_path):
     for name, file in (("sample", "sample_scene.json"), ("small", "small_scene.json")):
         W, H, bounces, sky, frames = (int(v) for v in gold[f"{name}_dims"])
         out = tmp_path / f"{name}.bin"
-        proc = subprocess.run([str(driver), "gpu", str(GOLDEN / file), str(W), str(H), str(bounces), str(sky), str(frames), str(out)],
-                              capture_output=True, text=True)
+        proc = subprocess.run([str(driver), "gpu", str(GOLDEN / file), str(W), str(H), str(bounces), str(sky), str(frames), str(out),
+                               str(tmp_path / name)], capture_output=True, text=True)
         assert proc.returncode == 0, proc.stdout + proc.stderr
         raw = np.fromfile(out, np.uint32)
         P = W * H
@@ -110,3 +110,14 @@ def test_cpp_renderer_bit_exact_vs_reference_cuda_golden(driver, tmp_path):
         assert (acc1 == gold[f"{name}_acc1"].view(np.uint32)).all()
         assert (accK == gold[f"{name}_accK"].view(np.uint32)).all()
         assert (rgba == gold[f"{name}_rgbaK"]).all()
+        # output sinks: PPM is the RGBA8 image flipped top to bottom, PFM the float radiance bottom row first
+        ppm = (tmp_path / f"{name}.ppm").read_bytes()
+        header = f"P6\n{W} {H}\n255\n".encode()
+        assert ppm.startswith(header)
+        rgb = np.frombuffer(ppm[len(header):], np.uint8).reshape(H, W, 3)
+        assert (rgb[::-1, :, 0] == (rgba & 0xFF)).all() and (rgb[::-1, :, 2] == ((rgba >> 16) & 0xFF)).all()
+        pfm = (tmp_path / f"{name}.pfm").read_bytes()
+        ph = f"PF\n{W} {H}\n-1.0\n".encode()
+        assert pfm.startswith(ph)
+        rad = np.frombuffer(pfm[len(ph):], np.float32).reshape(H, W, 3)
+        assert np.allclose(rad, accK.view(np.float32)[..., :3] / frames, rtol=1e-6, atol=0)
