@@ -6,11 +6,14 @@ missing this module raises: there is no Python or CPU fallback for the render pa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libataraxia_b200.so"
+if os.environ.get("ATX_LIB"):  # development: an experimental build of the same library (tools/build_variant.sh)
+    LIB_PATH = Path(os.environ["ATX_LIB"]).resolve()
 
 # every symbol include/ataraxia_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
@@ -28,7 +31,7 @@ ATX_OK = 0
 ATX_ERR_INVALID, ATX_ERR_CUDA, ATX_ERR_NCCL, ATX_ERR_NO_DEVICE, ATX_ERR_ALLOC = -1, -2, -3, -4, -5
 VARIANT_AUTO, VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1, 2
 TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD = 1, 2, 3, 4
-MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR = 0, 1, 2
+MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR, MEGA_WARP_QUEUE = 0, 1, 2, 3
 
 # numpy views of the reference PODs (SceneNode.h:11-21, Scene.h:17-47)
 SPHERE_DTYPE = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("material", "<i4")])

@@ -14,6 +14,7 @@
 // FP32 FMA pipe (sphere loop) and MUFU (shading); see DESIGN.md §5.
 #include "atx_device.cuh"
 #include "atx_kernels.h"
+#include <cstdio>
 
 namespace atxk
 {
@@ -606,6 +607,388 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 }
 
 // ---------------------------------------------------------------------------
+// Megakernel, warp-queue form (small scenes, many frames per launch).
+//
+// The while-while form above leaves lanes idle twice over: a lane whose path has a hit
+// waits for the bounce phase (which then runs with the 8-16 lanes that are parked), and the
+// frames of a pixel are strictly serial on their lane (measured on config 2: 17 of 32 lanes
+// active). Here every lane owns a pixel (claimed from the global pool, a few lanes at a time)
+// and the warp keeps two kinds of work apart, each close to full width:
+//   G  "generate": lane i starts the next frame of ITS pixel (the per-pixel constants of the
+//      launch - primary hit, and with one light the whole first bounce - stay in its
+//      registers) and traces that ray; a miss ends the path, a hit is pushed onto the warp's
+//      hit queue in shared memory (17 words: ray, color, throughput, seed, bounce, t, sphere,
+//      and a tag = owning lane + ring slot);
+//   B  "bounce": every lane pops ONE queued hit (any lane's pixel), runs the whole bounce -
+//      hit record, emission, shadow trace, Cook-Torrance, roulette, next direction - traces
+//      the continuing ray and pushes it back if it hits again.
+// A lane is never parked: after a hit it goes on with the next frame of its pixel. The
+// samples of a pixel therefore complete out of order, while the reference adds them in
+// frame order (accumulation[p] += color once per frame, Renderer.cu:165) and float sums do
+// not commute bit for bit. Each lane has a ring of kRingFrames sample slots in shared
+// memory; a finished path writes its color to its slot and sets the slot's bit, and the
+// owning lane adds completed slots to its running sum strictly in frame order (a sample
+// that completes while nothing older is pending goes straight to the sum). A lane whose
+// ring is full skips G until its oldest path has come back; B runs at once with 32 queued
+// hits and earlier when stalled lanes have cost as much as a narrow B would waste.
+// Measured on config 2 (1024 frames): G runs 28.9 lanes wide, B 28.4; 25.4 ms against the
+// while-while form's 31.1 ms. Shared memory (10.4 KB per warp) allows 20 warps per SM; a
+// 32-slot ring at 12 warps per SM is slower (32.5 ms), an 8-slot ring at 24 warps equal.
+// Same path_* code between traces as every other form, same frame order of the sums: the
+// results are bit-identical.
+// ---------------------------------------------------------------------------
+#ifndef ATX_RING
+#define ATX_RING 16
+#endif
+#ifndef ATX_WQ_CTAS
+#define ATX_WQ_CTAS 5
+#endif
+#ifndef ATX_WQ_BFULL
+#define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
+#endif
+constexpr uint32_t kRingFrames = ATX_RING;  // sample slots per pixel (power of two, <= 32: one done-bit each)
+constexpr uint32_t kQueueCap = 64;    // hit-queue entries per warp (G runs below 32, B pops 32 and pushes <= 32)
+constexpr uint32_t kQueueFields = 17;
+constexpr uint32_t kWqWarps = 4;      // warps per CTA
+constexpr uint32_t kWqWordsPerWarp = 3u * kRingFrames * 32u + 32u + kQueueFields * kQueueCap;
+
+#ifdef ATX_WQ_STATS
+// development build only: where the lanes of the warp-queue form go (printed by render_mega after each launch)
+__device__ unsigned long long g_wqStats[8];
+#define WQ_STAT(i, v) do { wqStat[i] += static_cast<unsigned long long>(v); } while (0)
+#else
+#define WQ_STAT(i, v) do { } while (0)
+#endif
+
+template <bool kFixedLight>
+__global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(const RenderParams p)
+{
+    extern __shared__ float4 smem[];
+    float4* sphS = smem;
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr uint32_t K = kRingFrames;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* warpWords = reinterpret_cast<uint32_t*>(smem + round_up8(p.nSpheres)) + (threadIdx.x >> 5) * kWqWordsPerWarp;
+    float* ring = reinterpret_cast<float*>(warpWords);   // [3][K][32]: channel, slot, pixel lane
+    uint32_t* done = warpWords + 3u * K * 32u;           // [32]: completed-slot bits per pixel lane
+    uint32_t* q = done + 32u;                            // [kQueueFields][kQueueCap]
+    float* qf = reinterpret_cast<float*>(q);
+
+    stage_spheres(sphS, p.spheres, p.nSpheres);
+    __syncthreads();
+
+    uint32_t rays = 0, traced = 0, paths = 0;
+#ifdef ATX_WQ_STATS
+    unsigned long long wqStat[8] = {};
+#endif
+
+    auto trace = [&](const PathState& s, float& tmin, int& closest) {
+        tmin = 3.402823466e+38f; // FLT_MAX
+        closest = -1;
+        const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+        trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+        traced++;
+    };
+    // a finished path hands its sample to the pixel's ring
+    auto complete = [&](uint32_t tag, const PathState& s) {
+        const uint32_t pl = tag & 31u, slot = tag >> 8;
+        ring[(0u * K + slot) * 32u + pl] = s.cr;
+        ring[(1u * K + slot) * 32u + pl] = s.cg;
+        ring[(2u * K + slot) * 32u + pl] = s.cb;
+        atomicOr(done + pl, 1u << slot);
+    };
+
+    // per-pixel state (lane = the pixel it owns until every frame of it is in the sum)
+    bool live = false;      // owns a pixel with frames to render through G/B
+    bool exhausted = false; // the pool has no more pixels
+    uint32_t pixel = 0, j = 0, head = 0; // frames started / frames added to the sum
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    V3 d0 = { 0.0f, 0.0f, 0.0f };
+    float tPrimary = 0.0f;
+    int cPrimary = -1;
+    uint32_t raysPerStart = 1;
+    float c0r = 0.0f, c0g = 0.0f, c0b = 0.0f, o0x = 0.0f, o0y = 0.0f, o0z = 0.0f;
+    V3 N0 = { 0.0f, 0.0f, 0.0f }, T0 = { 0.0f, 0.0f, 0.0f }, B0 = { 0.0f, 0.0f, 0.0f };
+    float pr0 = 0.0f, tq0x = 0.0f, tq0y = 0.0f, tq0z = 0.0f, ggxT0 = 0.0f;
+    bool ggx0 = false;
+    uint32_t qHead = 0u, qCount = 0u, stallDebt = 0u;
+    done[lane] = 0u;
+    __syncwarp();
+
+    // a lane that owns no pixel takes the next one of the pool: primary ray, its hit, and with one light
+    // the frame-independent first bounce. Claims are batched (claimThreshold idle lanes, or nothing else to
+    // do) so this prologue runs with several lanes; the first claim of a warp is a whole 8x4 tile.
+    auto claim = [&](uint32_t id) {
+        uint32_t x, y;
+        if (id >= p.poolSize)
+        {
+            exhausted = true;
+            return;
+        }
+        if (!pool_pixel(p, id, x, y))
+            return;
+        pixel = x + y * p.width;
+        acc = p.zeroFirst ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : p.accum[pixel];
+        bool store = false;
+        if (p.maxBounces < 1)
+        {
+            accumulate_black(acc, p.nFrames);
+            store = true;
+        }
+        else
+        {
+            // the pixel's primary ray and its hit: the same for every frame (Camera.cpp:176-187)
+            d0 = primary_direction(p.cam, x, y, p.width, p.height);
+            PathState s;
+            path_begin(s, p.cam.pos, d0, pixel, p.firstFrame);
+            trace(s, tPrimary, cPrimary);
+            if (cPrimary < 0)
+            {
+                accumulate_sky(p, acc, p.nFrames);
+                rays += p.nFrames;
+                store = true;
+            }
+            else
+            {
+                live = true;
+                j = 0u;
+                head = 0u;
+                raysPerStart = 1u;
+                if (kFixedLight)
+                {
+                    // one light (or none): the first bounce up to the roulette is frame-independent
+                    // (see megakernel_ww); run it once and keep what every frame starts from
+                    if (path_hit(p, s, sphS[cPrimary], cPrimary, tPrimary))
+                    {
+                        float tmin;
+                        int closest;
+                        trace(s, tmin, closest);
+                        path_shadow(p, s, closest, tmin);
+                        raysPerStart = 2u;
+                    }
+                    c0r = s.cr; c0g = s.cg; c0b = s.cb;
+                    o0x = s.ox; o0y = s.oy; o0z = s.oz;
+                    N0 = s.N;
+                    const float4 m0 = __ldg(p.mats + kMatStride * s.matIndex + 0);
+                    const float4 m1 = __ldg(p.mats + kMatStride * s.matIndex + 1);
+                    const float ax = fmul(1.0f, m0.x), ay = fmul(1.0f, m0.y), az = fmul(1.0f, m0.z);
+                    const float len = fsqrt_approx(fdot3(ax, ay, az, ax, ay, az));
+                    pr0 = fmax_(fmin_(len, 1.0f), 0.1f);
+                    tq0x = fdiv_approx(ax, pr0); tq0y = fdiv_approx(ay, pr0); tq0z = fdiv_approx(az, pr0);
+                    ggx0 = m1.w > 0.0f;
+                    ggxT0 = ggx0 ? __ldg(p.mats + kMatStride * s.matIndex + 5).x : 0.0f;
+                    tangent_frame(N0, T0, B0);
+                }
+            }
+        }
+        if (store)
+        {
+            p.accum[pixel] = acc;
+            if (p.emitRgba)
+                p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
+            paths += p.nFrames;
+        }
+    };
+
+    {
+        while (true)
+        {
+            // ---- add completed samples in frame order ----
+            if (live && head < j)
+            {
+                uint32_t d = done[lane];
+                while (head < j && ((d >> (head & (K - 1u))) & 1u))
+                {
+                    const uint32_t slot = head & (K - 1u);
+                    acc.x = fadd(ring[(0u * K + slot) * 32u + lane], acc.x);
+                    acc.y = fadd(ring[(1u * K + slot) * 32u + lane], acc.y);
+                    acc.z = fadd(ring[(2u * K + slot) * 32u + lane], acc.z);
+                    acc.w = fadd(acc.w, 1.0f);
+                    d &= ~(1u << slot);
+                    head++;
+                }
+                done[lane] = d;
+            }
+            if (live && head >= p.nFrames)
+            {
+                // every frame of the pixel is in the sum: st.global.v4.f32 + the display pack
+                p.accum[pixel] = acc;
+                if (p.emitRgba)
+                    p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
+                paths += p.nFrames;
+                live = false;
+            }
+            {
+                const bool need = !live && !exhausted;
+                const unsigned needMask = __ballot_sync(kFull, need);
+                if (needMask != 0u &&
+                    (static_cast<uint32_t>(__popc(needMask)) >= p.claimThreshold || (!__any_sync(kFull, live) && qCount == 0u)))
+                {
+                    const uint32_t id = pool_claim(p.pool, need);
+                    if (need)
+                        claim(id);
+                }
+            }
+            __syncwarp(); // the cleared bits are visible before another lane's bounce sets new ones
+            const bool wants = live && j < p.nFrames;
+            const bool gen = wants && (j - head) < K;
+            const unsigned genMask = __ballot_sync(kFull, gen);
+            const uint32_t nStalled = __popc(__ballot_sync(kFull, wants && !gen)); // ring full: waiting for an old path
+
+            PathState s;
+            bool wantPush = false;
+            float hitT = 0.0f;
+            int hitC = -1;
+            uint32_t tag = 0u;
+
+            // When to bounce: at once with 32 queued hits (a full warp). With fewer, B wastes (32 - n)/32 of
+            // its ~560 instructions, while every G iteration that passes with stalled lanes wastes 1/32 of
+            // its ~290 per stalled lane: run B when the stall debt has reached what a narrow B would waste
+            // (in lane-iterations: debt + 2n >= 64), the ski-rental rule, never worse than twice the optimum.
+            if (qCount != 0u && (genMask == 0u || stallDebt + 2u * qCount >= 2u * ATX_WQ_BFULL))
+            {
+                stallDebt = 0u;
+                WQ_STAT(4, 1); WQ_STAT(5, qCount < 32u ? qCount : 32u);
+                // ---- B: one bounce for up to 32 queued hits ----
+                const uint32_t n = qCount < 32u ? qCount : 32u;
+                if (lane < n)
+                {
+                    const uint32_t e = (qHead + lane) & (kQueueCap - 1u);
+                    s.ox = qf[0u * kQueueCap + e]; s.oy = qf[1u * kQueueCap + e]; s.oz = qf[2u * kQueueCap + e];
+                    s.dx = qf[3u * kQueueCap + e]; s.dy = qf[4u * kQueueCap + e]; s.dz = qf[5u * kQueueCap + e];
+                    s.cr = qf[6u * kQueueCap + e]; s.cg = qf[7u * kQueueCap + e]; s.cb = qf[8u * kQueueCap + e];
+                    s.tx = qf[9u * kQueueCap + e]; s.ty = qf[10u * kQueueCap + e]; s.tz = qf[11u * kQueueCap + e];
+                    s.seed = q[12u * kQueueCap + e];
+                    s.bounce = static_cast<int>(q[13u * kQueueCap + e]);
+                    const float t = qf[14u * kQueueCap + e];
+                    const int c = static_cast<int>(q[15u * kQueueCap + e]);
+                    tag = q[16u * kQueueCap + e];
+                    if (path_hit(p, s, sphS[c], c, t))
+                    {
+                        float tmin;
+                        int closest;
+                        trace(s, tmin, closest);
+                        rays++;
+                        path_shadow(p, s, closest, tmin);
+                    }
+                    bool ended = path_bounce(p, s);
+                    if (!ended)
+                    {
+                        trace(s, hitT, hitC);
+                        rays++;
+                        if (hitC >= 0)
+                            wantPush = true;
+                        else
+                        {
+                            path_miss(p, s);
+                            ended = true;
+                        }
+                    }
+                    if (ended)
+                        complete(tag, s);
+                }
+                qHead = (qHead + n) & (kQueueCap - 1u);
+                qCount -= n;
+            }
+            else if (genMask != 0u)
+            {
+                // ---- G: the next frame of this lane's pixel ----
+                stallDebt += nStalled;
+                WQ_STAT(0, 1); WQ_STAT(1, __popc(genMask)); WQ_STAT(2, nStalled);
+                WQ_STAT(3, __popc(__ballot_sync(kFull, live && j >= p.nFrames)));
+                if (gen)
+                {
+                    const uint32_t frame = p.firstFrame + j * p.frameStride;
+                    tag = lane | ((j & (K - 1u)) << 8);
+                    rays += raysPerStart;
+                    bool flying = false;
+                    if (!kFixedLight)
+                    {
+                        // the path starts at the cached primary hit: straight to the bounce queue
+                        path_begin(s, p.cam.pos, d0, pixel, frame);
+                        wantPush = true;
+                        hitT = tPrimary;
+                        hitC = cPrimary;
+                    }
+                    else
+                    {
+                        // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in
+                        s.cr = c0r; s.cg = c0g; s.cb = c0b;
+                        s.seed = pixel * frame;
+                        if (!(pcg_float(s.seed) > pr0))
+                        {
+                            float lx, ly, lz;
+                            sample_local(ggx0, ggxT0, s.seed, lx, ly, lz);
+                            const V3 nd = frame_combine(N0, T0, B0, lx, ly, lz);
+                            if (1 < p.maxBounces)
+                            {
+                                s.ox = o0x; s.oy = o0y; s.oz = o0z;
+                                s.dx = nd.x; s.dy = nd.y; s.dz = nd.z;
+                                s.tx = tq0x; s.ty = tq0y; s.tz = tq0z;
+                                s.bounce = 1;
+                                s.seed += 1u; // Renderer.cu:306
+                                flying = true;
+                            }
+                        }
+                        if (flying)
+                        {
+                            trace(s, hitT, hitC);
+                            rays++;
+                            if (hitC >= 0)
+                                wantPush = true;
+                            else
+                                path_miss(p, s);
+                        }
+                    }
+                    if (!wantPush)
+                    {
+                        // the path is complete: straight to the sum when nothing older is pending
+                        if (head == j)
+                        {
+                            accumulate_sample(acc, s);
+                            head++;
+                        }
+                        else
+                            complete(tag, s);
+                    }
+                    j++;
+                }
+            }
+            else if (__all_sync(kFull, exhausted && !live))
+                break; // no pixel left anywhere in the warp
+            else
+                continue; // pixels were just retired or claimed: look again
+
+            // ---- push the rays that hit (converged: every lane takes part in the ballot) ----
+            __syncwarp();
+            const unsigned pushMask = __ballot_sync(kFull, wantPush);
+            if (wantPush)
+            {
+                const uint32_t e = (qHead + qCount + __popc(pushMask & ((1u << lane) - 1u))) & (kQueueCap - 1u);
+                qf[0u * kQueueCap + e] = s.ox; qf[1u * kQueueCap + e] = s.oy; qf[2u * kQueueCap + e] = s.oz;
+                qf[3u * kQueueCap + e] = s.dx; qf[4u * kQueueCap + e] = s.dy; qf[5u * kQueueCap + e] = s.dz;
+                qf[6u * kQueueCap + e] = s.cr; qf[7u * kQueueCap + e] = s.cg; qf[8u * kQueueCap + e] = s.cb;
+                qf[9u * kQueueCap + e] = s.tx; qf[10u * kQueueCap + e] = s.ty; qf[11u * kQueueCap + e] = s.tz;
+                q[12u * kQueueCap + e] = s.seed;
+                q[13u * kQueueCap + e] = static_cast<uint32_t>(s.bounce);
+                qf[14u * kQueueCap + e] = hitT;
+                q[15u * kQueueCap + e] = static_cast<uint32_t>(hitC);
+                q[16u * kQueueCap + e] = tag;
+            }
+            qCount += __popc(pushMask);
+            __syncwarp();
+        }
+
+    }
+#ifdef ATX_WQ_STATS
+    if (lane == 0u)
+        for (int i = 0; i < 8; i++)
+            atomicAdd(&g_wqStats[i], wqStat[i]);
+#endif
+    count_rays(p, rays, traced, paths);
+}
+
+// ---------------------------------------------------------------------------
 // Megakernel, two-slot packed form (large scenes: the sphere loop dominates).
 //
 // One thread = two path slots, each rendering a claimed pixel. The path loop of
@@ -954,9 +1337,18 @@ int mega_kind(const RenderParams& p, int requested)
     const bool chunked = p.chunkSpheres < p.nSpheres;
     if (chunked)
         return kMegaPair;
-    if (requested == kMegaWhileWhile || requested == kMegaPair)
+    if (requested == kMegaWhileWhile || requested == kMegaPair || requested == kMegaWarpQueue)
         return requested;
-    return p.nSpheres <= kWhileWhileMaxSpheres ? kMegaWhileWhile : kMegaPair;
+    if (p.nSpheres > kWhileWhileMaxSpheres)
+        return kMegaPair;
+    // few frames per launch: a tile is over before the hit queue ever fills, and the drain runs at the
+    // width the while-while form has anyway
+    return p.nFrames >= kWarpQueueMinFrames ? kMegaWarpQueue : kMegaWhileWhile;
+}
+
+static size_t warp_queue_smem_bytes(const RenderParams& p)
+{
+    return sizeof(float4) * ((static_cast<size_t>(p.nSpheres) + 7u) & ~size_t(7)) + sizeof(uint32_t) * kWqWordsPerWarp * kWqWarps;
 }
 
 size_t megakernel_smem_bytes(const RenderParams& p)
@@ -978,7 +1370,13 @@ cudaError_t configure()
     e = cudaFuncSetAttribute(megakernel_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    e = cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    e = cudaFuncSetAttribute(megakernel_wq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(megakernel_wq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
 }
 
 cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream_t s)
@@ -987,6 +1385,37 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
     const size_t smem = megakernel_smem_bytes(p);
     // persistent CTAs: as many as stay resident (3 or 2 per SM), fewer for tiny images
     const uint32_t byWork = (p.poolSize + 255u) / 256u;
+    if (mega_kind(p, kind) == kMegaWarpQueue)
+    {
+        const size_t wq = warp_queue_smem_bytes(p);
+        if (wq > static_cast<size_t>(kMaxSmemBytes))
+            return cudaErrorInvalidValue;
+        int perSm = 0;
+        cudaError_t e = p.nLights <= 1u
+                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, megakernel_wq<true>, kWqWarps * 32, wq)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, megakernel_wq<false>, kWqWarps * 32, wq);
+        if (e != cudaSuccess)
+            return e;
+        // no more CTAs than the image has 8x4 tiles per warp
+        const uint32_t tiles = p.poolSize / 32u;
+        const uint32_t grid = max(1u, min(static_cast<uint32_t>(smCount * max(perSm, 1)), (tiles + kWqWarps - 1u) / kWqWarps));
+        if (p.nLights <= 1u)
+            megakernel_wq<true><<<grid, kWqWarps * 32, wq, s>>>(p);
+        else
+            megakernel_wq<false><<<grid, kWqWarps * 32, wq, s>>>(p);
+#ifdef ATX_WQ_STATS
+        {
+            unsigned long long st[8], zero[8] = {};
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(st, g_wqStats, sizeof(st));
+            cudaMemcpyToSymbol(g_wqStats, zero, sizeof(zero));
+            fprintf(stderr, "wq stats: G iters %llu, lanes generating %.2f, stalled %.2f, finished %.2f | B iters %llu, lanes %.2f\n", st[0],
+                    double(st[1]) / double(st[0] ? st[0] : 1), double(st[2]) / double(st[0] ? st[0] : 1),
+                    double(st[3]) / double(st[0] ? st[0] : 1), st[4], double(st[5]) / double(st[4] ? st[4] : 1));
+        }
+#endif
+        return cudaGetLastError();
+    }
     if (mega_kind(p, kind) == kMegaWhileWhile)
     {
         const uint32_t grid = min(static_cast<uint32_t>(smCount) * 3u, byWork);

@@ -20,7 +20,9 @@ constexpr int kSmemBudgetTwoCtas = 72 * 1024; // sphere records; + 32 KB candida
 constexpr int kMegaAuto = 0;
 constexpr int kMegaWhileWhile = 1; // one pixel per thread, hits gathered before the shading phase
 constexpr int kMegaPair = 2;       // two pixels per thread, packed f32x2 sphere loop
+constexpr int kMegaWarpQueue = 3;  // one tile per warp, hits queued in shared memory and bounced 32 at a time
 constexpr uint32_t kWhileWhileMaxSpheres = 16;
+constexpr uint32_t kWarpQueueMinFrames = 32; // frames per launch from which the warp-queue form replaces the while-while form
 
 cudaError_t configure();
 int mega_kind(const atxk::RenderParams& p, int requested);

@@ -114,6 +114,48 @@ namespace atx
                  x.x * y.y - y.x * x.y };
     }
 
+    // ---- quaternion slice used by Camera::onUpdate (Camera.cpp:88-96) ----
+    inline vec2 operator-(const vec2& a, const vec2& b) { return { a.x - b.x, a.y - b.y }; }
+
+    // ext/quaternion_trigonometric.inl:30-36 — s = sin(a/2) first, then (cos(a/2), v*s)
+    inline quat angleAxis(float angle, const vec3& v)
+    {
+        const float s = std::sin(angle * 0.5f);
+        const vec3 vs = v * s;
+        return quat(std::cos(angle * 0.5f), vs.x, vs.y, vs.z);
+    }
+
+    // ext/quaternion_geometric.inl:27-34
+    inline quat cross(const quat& q1, const quat& q2)
+    {
+        return quat(q1.w * q2.w - q1.x * q2.x - q1.y * q2.y - q1.z * q2.z,
+                    q1.w * q2.x + q1.x * q2.w + q1.y * q2.z - q1.z * q2.y,
+                    q1.w * q2.y + q1.y * q2.w + q1.z * q2.x - q1.x * q2.z,
+                    q1.w * q2.z + q1.z * q2.w + q1.x * q2.y - q1.y * q2.x);
+    }
+
+    // detail/type_quat.inl:17-24 — (w*w + x*x) + (y*y + z*z)
+    inline float dot(const quat& a, const quat& b) { return (a.w * b.w + a.x * b.x) + (a.y * b.y + a.z * b.z); }
+
+    // ext/quaternion_geometric.inl:11-24
+    inline quat normalize(const quat& q)
+    {
+        const float len = std::sqrt(dot(q, q));
+        if (len <= 0.0f)
+            return quat(1.0f, 0.0f, 0.0f, 0.0f);
+        const float oneOverLen = 1.0f / len;
+        return quat(q.w * oneOverLen, q.x * oneOverLen, q.y * oneOverLen, q.z * oneOverLen);
+    }
+
+    // detail/type_quat.inl:359-366 (what gtx/quaternion.inl:51-54 rotate() returns): v + ((uv*w) + uuv) * 2
+    inline vec3 rotate(const quat& q, const vec3& v)
+    {
+        const vec3 qv(q.x, q.y, q.z);
+        const vec3 uv = cross(qv, v);
+        const vec3 uuv = cross(qv, uv);
+        return v + ((uv * q.w) + uuv) * 2.0f;
+    }
+
     // detail/func_trigonometric.inl:9-14
     inline float radians(float degrees) { return degrees * static_cast<float>(0.01745329251994329576923690768489); }
 
@@ -291,6 +333,8 @@ namespace glm
     using atx::normalize;
     using atx::perspective;
     using atx::radians;
+    using atx::angleAxis;
+    using atx::rotate;
     using atx::scale;
     using atx::translate;
 }

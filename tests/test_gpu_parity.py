@@ -141,7 +141,7 @@ def _live_compare(atx, scene_path, W, H, bounces, sky, frames):
 
 
 @pytest.mark.parametrize("W,H,bounces,sky,frames", [(333, 127, 5, False, 3), (640, 360, 8, True, 16), (64, 64, 1, False, 2),
-                                                    (8, 4, 25, True, 5)])
+                                                    (8, 4, 25, True, 5), (320, 180, 8, False, 48)])  # 48 frames: warp-queue form
 def test_live_sample_scene(atx, W, H, bounces, sky, frames):
     _live_compare(atx, GOLDEN / "sample_scene.json", W, H, bounces, sky, frames)
 
@@ -254,6 +254,36 @@ def test_megakernel_forms_are_bit_identical(atx):
                 ref = (acc, c.rays)
             assert (bits(acc) == bits(ref[0])).all(), (kind, rounds, W, H)
             assert c.rays == ref[1]
+        r.close()
+
+
+def test_warp_queue_form_is_bit_identical(atx):
+    """Warp-queue form (one tile per warp, hits bounced 32 at a time, samples re-ordered through the per-pixel
+    ring) against the while-while form: same bits and ray counts for 1 light (first bounce cached), several
+    lights and none, sky on/off, frame counts below / at / far above the ring size, strided frames starting from
+    a non-zero sum, bounce limits 1 and 25, partial tiles."""
+    cases = [(atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 161, 91, 8, False, 70),
+             (atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 64, 36, 25, True, 200),
+             (atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 40, 20, 1, True, 33),
+             (atx.synthetic.small(8, 1, seed=6), 64, 40, 8, False, 17),
+             (atx.synthetic.small(12, 3, seed=9), 97, 55, 8, True, 48),
+             (atx.synthetic.small(16, 0, seed=7), 80, 48, 5, True, 40),
+             (atx.synthetic.small(5, 2, seed=3), 33, 9, 6, False, 1)]
+    for scene, W, H, bounces, sky, frames in cases:
+        r, cam = setup(atx, scene, W, H, bounces, sky)
+        r.uploadScene(scene); r.setCamera(cam)
+        out = []
+        for kind in (atx.MEGA_WHILE_WHILE, atx.MEGA_WARP_QUEUE):
+            r.setTuning(atx.TUNE_MEGA_KIND, kind)
+            r.resetCounters()
+            r.renderFrames(1, frames, 1, zero_first=True)
+            r.renderFrames(3, frames // 2 + 1, 5, zero_first=False)      # continues the stored sums, strided frames
+            c = r.counters()
+            out.append((r.getAccumulation(), r.getRGBA8(divisor=7), c.paths, c.rays, c.rays_traced))
+        assert (out[0][0][..., 3] == frames + frames // 2 + 1).all()
+        assert (bits(out[0][0]) == bits(out[1][0])).all(), (W, H, bounces, frames)
+        assert (out[0][1] == out[1][1]).all()
+        assert out[0][2:] == out[1][2:], (W, H, bounces, frames, out[0][2:], out[1][2:])
         r.close()
 
 
