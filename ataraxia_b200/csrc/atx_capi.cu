@@ -477,10 +477,10 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
         return fail(ATX_ERR_INVALID, "shared-memory plan exceeds the device limit");
     // pixel claims: whole 8x4 tiles for the while-while form (its lockstep lives on coherent warps), small
     // batches for the packed form (the sphere loop does not care which pixels share a warp) and for the
-    // warp-queue form (measured on config 2: 4 idle lanes per claim, 25.4 ms; 1: 25.7; 8: 25.8)
+    // warp-queue form (measured on config 2: 3-4 idle lanes per claim are best, 1 or 8 cost 1-2 %)
     const int formKind = atx_launch::mega_kind(p, h->megaKind);
     p.claimThreshold = h->claimThreshold ? h->claimThreshold
-                                         : (formKind == atx_launch::kMegaWhileWhile ? 32u : formKind == atx_launch::kMegaWarpQueue ? 4u : 2u);
+                                         : (formKind == atx_launch::kMegaWhileWhile ? 32u : formKind == atx_launch::kMegaWarpQueue ? 3u : 2u);
     ATX_CUDA(cudaMemsetAsync(h->dPool, 0, sizeof(uint32_t), h->stream));
     ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->smCount, h->stream));
     h->launches++;

@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 // that completes while nothing older is pending goes straight to the sum). A lane whose
 // ring is full skips G until its oldest path has come back; B runs at once with 32 queued
 // hits and earlier when stalled lanes have cost as much as a narrow B would waste.
-// Measured on config 2 (1024 frames): G runs 28.9 lanes wide, B 28.4; 25.4 ms against the
+// Measured on config 2 (1024 frames): G runs 28.9 lanes wide, B 28.4; 24.4 ms against the
 // while-while form's 31.1 ms. Shared memory (10.4 KB per warp) allows 20 warps per SM; a
 // 32-slot ring at 12 warps per SM is slower (32.5 ms), an 8-slot ring at 24 warps equal.
 // Same path_* code between traces as every other form, same frame order of the sums: the
@@ -642,6 +642,9 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 #endif
 #ifndef ATX_WQ_CTAS
 #define ATX_WQ_CTAS 5
+#endif
+#ifndef ATX_WQ_BOOKKEEP
+#define ATX_WQ_BOOKKEEP 7u // retire/claim check every 8th pass of the warp loop (power of two minus one; measured: every pass 25.5 ms, 4th 24.7, 8th 24.5)
 #endif
 #ifndef ATX_WQ_BFULL
 #define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
@@ -711,7 +714,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     V3 N0 = { 0.0f, 0.0f, 0.0f }, T0 = { 0.0f, 0.0f, 0.0f }, B0 = { 0.0f, 0.0f, 0.0f };
     float pr0 = 0.0f, tq0x = 0.0f, tq0y = 0.0f, tq0z = 0.0f, ggxT0 = 0.0f;
     bool ggx0 = false;
-    uint32_t qHead = 0u, qCount = 0u, stallDebt = 0u;
+    uint32_t qHead = 0u, qCount = 0u, stallDebt = 0u, pass = 0u;
     done[lane] = 0u;
     __syncwarp();
 
@@ -809,6 +812,10 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 }
                 done[lane] = d;
             }
+            // retiring and claiming pixels is looked at every (ATX_WQ_BOOKKEEP + 1)th pass: a finished lane idles
+            // for at most that many of its pixel's nFrames passes
+            if ((pass++ & ATX_WQ_BOOKKEEP) == 0u)
+            {
             if (live && head >= p.nFrames)
             {
                 // every frame of the pixel is in the sum: st.global.v4.f32 + the display pack
@@ -828,6 +835,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     if (need)
                         claim(id);
                 }
+            }
             }
             __syncwarp(); // the cleared bits are visible before another lane's bounce sets new ones
             const bool wants = live && j < p.nFrames;
