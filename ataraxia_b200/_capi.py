@@ -25,6 +25,7 @@ SYMBOLS = [
     "atx_get_counters", "atx_reset_counters", "atx_accum_device_ptr", "atx_stream",
     "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum",
     "atx_host_camera_matrices", "atx_host_ray_directions", "atx_host_node_transform", "atx_host_transform_sphere", "atx_host_mat4_mul",
+    "atx_host_camera_update",
 ]
 
 ATX_OK = 0
@@ -50,6 +51,14 @@ class AtxError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"ataraxia_b200 error {status}: {message}")
         self.status = status
+
+
+KEY_W, KEY_S, KEY_A, KEY_D, KEY_Q, KEY_E = 1, 2, 4, 8, 16, 32
+
+
+class CameraInput(C.Structure):
+    """atx_camera_input (include/ataraxia_b200.h): what Camera::onUpdate reads from the window."""
+    _fields_ = [("keys", C.c_uint32), ("right_button", C.c_uint32), ("mouse_x", C.c_float), ("mouse_y", C.c_float)]
 
 
 _lib = None
@@ -105,6 +114,7 @@ def lib() -> C.CDLL:
         "atx_host_node_transform": [fp, fp, fp, fp, fp, fp],
         "atx_host_transform_sphere": [fp, vp, vp],
         "atx_host_mat4_mul": [fp, fp, fp],
+        "atx_host_camera_update": [fp, fp, fp, C.POINTER(CameraInput), C.c_float, C.POINTER(C.c_int)],
     }
     for name, argtypes in sig.items():
         fn = getattr(l, name)

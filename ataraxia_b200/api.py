@@ -127,8 +127,25 @@ def _mat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return out
 
 
+@dataclass
+class InputState:
+    """What Camera::onUpdate asks the window for (Core/include/input/Input.h:11-16), as plain data so that
+    camera motion can be scripted: keys is a string of the pressed keys among "WASDQE", mouse the cursor
+    position, right_button whether MouseButton::Right is held (the reference only moves the camera then)."""
+    keys: str = ""
+    mouse: Sequence[float] = (0.0, 0.0)
+    right_button: bool = False
+
+    def pack(self) -> _capi.CameraInput:
+        bits = {"W": _capi.KEY_W, "S": _capi.KEY_S, "A": _capi.KEY_A, "D": _capi.KEY_D, "Q": _capi.KEY_Q, "E": _capi.KEY_E}
+        mask = 0
+        for k in self.keys.upper():
+            mask |= bits[k]
+        return _capi.CameraInput(mask, int(bool(self.right_button)), float(self.mouse[0]), float(self.mouse[1]))
+
+
 class Camera:
-    """Camera.h:14-88 / Camera.cpp. Input handling (onUpdate) is out of scope (needs a window)."""
+    """Camera.h:14-88 / Camera.cpp. onUpdate takes the input as data (InputState) instead of polling GLFW."""
 
     def __init__(self, fov: Optional[float] = None, nearClip: float = 0.1, farClip: float = 100.0,
                  position=None, direction=None):
@@ -142,6 +159,7 @@ class Camera:
         self.m_fov, self.m_nearClip, self.m_farClip = 45.0, 0.1, 100.0
         self.m_width = self.m_height = 0
         self.m_viewDirty = self.m_projectionDirty = True
+        self.m_lastMousePos = np.zeros(2, np.float32)  # Camera.h:83
         if fov is not None:
             # Camera.cpp:14-29: both value constructors preset 1600x900 and build both matrices
             self.m_fov, self.m_nearClip, self.m_farClip = float(fov), float(nearClip), float(farClip)
@@ -168,6 +186,30 @@ class Camera:
     def getInverseProjectionMatrix(self): return self.m_inverseProjectionMatrix
     @staticmethod
     def getRotationSpeed(): return 0.3
+
+    def onUpdate(self, ts: float, inp: Optional[InputState] = None) -> bool:
+        """Camera::onUpdate (Camera.cpp:30-108): W/S, A/D, Q/E at speed 5 and mouse look at rotation speed 0.3
+        while the right button is held; returns whether the camera moved. The arithmetic runs in the library
+        (atx_host_camera_update) in glm's evaluation order."""
+        inp = inp or InputState()
+        moved = C.c_int(0)
+        packed = inp.pack()
+        check(_capi.lib().atx_host_camera_update(fptr(self.m_position), fptr(self.m_direction), fptr(self.m_lastMousePos),
+                                                 C.byref(packed), float(ts), C.byref(moved)))
+        if moved.value:
+            self.m_viewDirty = True
+        if self.m_viewDirty and inp.right_button:   # :101-105 (not reached when the button is up, :36-40)
+            self._updateViewMatrix()
+            self.m_rayDirection = None
+        return bool(moved.value)
+
+    def copy(self) -> "Camera":
+        """Value copy, like `m_scene.camera = m_camera` (Camera.h:20-38)."""
+        c = Camera()
+        for k, v in self.__dict__.items():
+            setattr(c, k, v.copy() if isinstance(v, np.ndarray) else v)
+        c.m_rayDirection = None
+        return c
 
     def Resize(self, width: int, height: int):
         """Camera.cpp:110-127 (including the early return that leaves a 1600x900 camera without rays)."""
@@ -444,3 +486,162 @@ class Renderer:
 
     def commDestroy(self): check(_capi.lib().atx_comm_destroy(self._h))
     def allreduceAccum(self): check(_capi.lib().atx_allreduce_accum(self._h))
+
+
+class Ataraxia:
+    """Headless mirror of the `Ataraxia` layer (Engine/src/main.cpp:8-283): what the application does AROUND
+    Renderer::Render, i.e. the caller-side semantics a user of the path sees without the window.
+
+      onUpdate(ts, input)   main.cpp:22-32: camera motion resets the accumulation; global transforms refreshed
+      Render(frames)        main.cpp:211-220: onResize, camera.Resize, Renderer::Render, wall-clock "Last Render Time"
+      ImportScene/ExportScene  main.cpp:196-209
+      the UI widgets of onGuiRender (main.cpp:34-176) as methods, each with the widget's own reset behaviour:
+      node / sphere / camera edits call resetFrameIndex(); material, light, "Sky Light" and "Ray Depth" edits do
+      NOT (main.cpp:44-45, 146-176) — and since the scene is only re-uploaded when frameIndex == 1
+      (Renderer.cu:175-179), material and light edits stay invisible until the next reset. That is the
+      reference's behaviour and the default here; `eagerEdits=True` resets on those edits too.
+    """
+
+    def __init__(self, device: int = 0, eagerEdits: bool = False):
+        import time as _time
+        self._clock = _time.perf_counter
+        self.m_camera = Camera(45.0, 0.1, 100.0)
+        self.m_renderer = Renderer(device)
+        self.m_scene = Scene()
+        self.m_scene.camera = self.m_camera.copy()
+        self.m_scene.settings = self.m_renderer.getSettings()
+        self.m_viewportWidth = self.m_viewportHeight = 0
+        self.m_lastRenderTime = 0.0
+        self.eagerEdits = eagerEdits
+        self._initializeScene()
+
+    def close(self):
+        self.m_renderer.close()
+
+    # ---- Layer interface ------------------------------------------------------
+    def onUpdate(self, ts: float, inp: Optional[InputState] = None):
+        if self.m_camera.onUpdate(ts, inp):
+            self.m_renderer.resetFrameIndex()
+            self.m_scene.camera = self.m_camera.copy()
+            self.m_scene.settings = self.m_renderer.getSettings()
+        self.m_scene.rootNode.updateGlobalTransform()
+
+    def setViewport(self, width: int, height: int):
+        """ImGui::GetContentRegionAvail of the "Viewport" window (main.cpp:181-182)."""
+        self.m_viewportWidth, self.m_viewportHeight = int(width), int(height)
+
+    def Render(self, frames: int = 1, readback: bool = True):
+        t0 = self._clock()
+        self.m_renderer.onResize(self.m_viewportWidth, self.m_viewportHeight)
+        self.m_camera.Resize(self.m_viewportWidth, self.m_viewportHeight)
+        self.m_renderer.Render(self.m_camera, self.m_scene, frames=frames, readback=readback)
+        self.m_lastRenderTime = (self._clock() - t0) * 1e3
+
+    def ImportScene(self, path: str = "scene.json"):
+        from . import utils
+        self.m_scene = utils.importScene(path)
+        self.m_camera = self.m_scene.camera.copy()
+        self.m_renderer.setSettings(self.m_scene.settings)
+        self.m_renderer.resetFrameIndex()
+
+    def ExportScene(self, path: str = "scene.json"):
+        from . import utils
+        self.m_scene.camera = self.m_camera.copy()
+        self.m_scene.settings = self.m_renderer.getSettings()
+        utils.exportScene(self.m_scene, path)
+
+    def GetRenderer(self): return self.m_renderer
+    def GetScene(self): return self.m_scene
+    def SetScene(self, scene: Scene): self.m_scene = scene
+    def lastRenderTimeMs(self) -> float: return self.m_lastRenderTime
+
+    # ---- "Settings" window (main.cpp:38-66) -------------------------------------
+    def setAccumulation(self, on: bool): self.m_renderer.getSettings().accumulation = bool(on)
+    def resetFrameIndex(self): self.m_renderer.resetFrameIndex()
+
+    def setSkyLight(self, on: bool):
+        self.m_renderer.getSettings().skyLight = bool(on)
+        self._edited()
+
+    def setMaxBounces(self, n: int):
+        self.m_renderer.getSettings().maxBounces = max(1, min(500, int(n)))  # DragInt range, main.cpp:45
+        self._edited()
+
+    def setFov(self, fov: float):
+        self.m_camera = Camera(float(fov), 0.1, 100.0, self.m_camera.getPosition(), self.m_camera.getDirection())
+        self.m_scene.camera = self.m_camera.copy()
+        self.m_renderer.resetFrameIndex()
+
+    def resetCamera(self):
+        self.m_camera = Camera(45.0, 0.1, 100.0)
+        self.m_scene.camera = self.m_camera.copy()
+        self.m_renderer.resetFrameIndex()
+
+    # ---- "Hierarchy" window (main.cpp:75-143) and the "Add" menu (:292-300) ----------
+    def setNodePosition(self, node: SceneNode, p): node.setPosition(p); self.m_renderer.resetFrameIndex()
+    def setNodeRotation(self, node: SceneNode, q_xyzw): node.setRotation(q_xyzw); self.m_renderer.resetFrameIndex()
+    def setNodeScale(self, node: SceneNode, s): node.setScale(s); self.m_renderer.resetFrameIndex()
+
+    def removeNode(self, node: SceneNode):
+        self.m_scene.rootNode.removeChild(node)   # only direct children of the root are found (main.cpp:105)
+        self.m_renderer.resetFrameIndex()
+
+    def setSphereCenter(self, node: SceneNode, index: int, c): node.getSpheres()[index].center = tuple(_vec3(c)); self.m_renderer.resetFrameIndex()
+    def setSphereRadius(self, node: SceneNode, index: int, r: float): node.getSpheres()[index].radius = float(r); self.m_renderer.resetFrameIndex()
+    def setSphereMaterial(self, node: SceneNode, index: int, m: int): node.getSpheres()[index].id = int(m); self.m_renderer.resetFrameIndex()
+
+    def addSphere(self):
+        """Menu "Add > Sphere" (main.cpp:294-298): no reset — it shows up at the next one."""
+        self.m_scene.rootNode.addSphere(Sphere((0.0, 0.0, 0.0), 1.0, 0))
+        self._edited()
+
+    # ---- "Material settings" / "Light settings" (main.cpp:145-176): no reset in the reference ----
+    def editMaterial(self, index: int, **fields):
+        for k, v in fields.items():
+            if not hasattr(self.m_scene.materials[index], k):
+                raise AttributeError(k)
+            setattr(self.m_scene.materials[index], k, v)
+        self._edited()
+
+    def editLight(self, index: int, **fields):
+        for k, v in fields.items():
+            if not hasattr(self.m_scene.lights[index], k):
+                raise AttributeError(k)
+            setattr(self.m_scene.lights[index], k, v)
+        self._edited()
+
+    def _edited(self):
+        if self.eagerEdits:
+            self.m_renderer.resetFrameIndex()
+
+    # ---- scripted camera path ------------------------------------------------------
+    def playCameraPath(self, steps, frames_per_step: int = 1, on_frame=None):
+        """Run a scripted sequence of (ts, InputState) through onUpdate + Render, as the main loop would
+        (Application::run: onUpdate, then onGuiRender -> Render, once per UI frame). `on_frame(i, app)` is called
+        after every step; returns the frame index after each step."""
+        out = []
+        for i, (ts, inp) in enumerate(steps):
+            self.onUpdate(ts, inp)
+            self.Render(frames_per_step)
+            out.append(self.m_renderer.frameIndex())
+            if on_frame is not None:
+                on_frame(i, self)
+        return out
+
+    def _initializeScene(self):
+        """main.cpp:234-265."""
+        root = self.m_scene.rootNode
+        root.addSphere(Sphere((0.0, 0.0, 0.0), 1.0, 0))
+        child = SceneNode("ChildNode1")
+        child.setPosition((2.0, 0.0, 0.0))
+        child.addSphere(Sphere((0.0, 0.0, 0.0), 1.0, 1))
+        root.addChild(child)
+        grand = SceneNode("GrandChildNode")
+        grand.setPosition((0.0, 2.0, 0.0))
+        grand.addSphere(Sphere((0.0, 0.0, 0.0), 1.0, 2))
+        child.addChild(grand)
+        # Material(albedo, roughness, metallic, emissionColor, emissionIntensity, id): F0 keeps its 0.04 default (Scene.h:43-46)
+        self.m_scene.materials.append(Material(albedo=(1.022, 0.782, 0.344), roughness=1.0, metallic=0.0, id=0))
+        self.m_scene.materials.append(Material(albedo=(1.0, 0.0, 0.0), roughness=0.3, metallic=0.0, id=1))
+        self.m_scene.materials.append(Material(albedo=(0.972, 0.960, 0.915), roughness=0.25, metallic=1.0, id=2))
+        self.m_scene.lights.append(Light((10.0, 10.0, 0.0), (1.0, 1.0, 1.0), 1.0))

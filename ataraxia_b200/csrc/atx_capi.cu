@@ -933,4 +933,45 @@ atx_status atx_host_transform_sphere(const float global[16], const atx_sphere* i
     return ATX_OK;
 }
 
+atx_status atx_host_camera_update(float position[3], float direction[3], float last_mouse[2], const atx_camera_input* input,
+                                  float dt, int* moved)
+{
+    // Camera::onUpdate (Camera.cpp:30-108), statement for statement
+    if (!position || !direction || !last_mouse || !input)
+        return fail(ATX_ERR_INVALID, "null argument");
+    atx::vec3 pos(position[0], position[1], position[2]), dir(direction[0], direction[1], direction[2]);
+    const atx::vec2 mousePos(input->mouse_x, input->mouse_y);
+    const atx::vec2 mouseDelta = (mousePos - atx::vec2(last_mouse[0], last_mouse[1])) * 0.002f;
+    last_mouse[0] = mousePos.x;
+    last_mouse[1] = mousePos.y;
+    if (moved)
+        *moved = 0;
+    if (!input->right_button)
+        return ATX_OK; // :36-40
+    bool didMove = false;
+    const atx::vec3 up(0.0f, 1.0f, 0.0f);
+    const atx::vec3 right = atx::cross(dir, up);
+    const float speed = 5.0f;
+    if (input->keys & ATX_KEY_W) { pos += dir * speed * dt; didMove = true; }
+    else if (input->keys & ATX_KEY_S) { pos -= dir * speed * dt; didMove = true; }
+    if (input->keys & ATX_KEY_A) { pos -= right * speed * dt; didMove = true; }
+    else if (input->keys & ATX_KEY_D) { pos += right * speed * dt; didMove = true; }
+    if (input->keys & ATX_KEY_Q) { pos -= up * speed * dt; didMove = true; }
+    else if (input->keys & ATX_KEY_E) { pos += up * speed * dt; didMove = true; }
+    if (mouseDelta.x != 0.0f || mouseDelta.y != 0.0f)
+    {
+        const float yaw = mouseDelta.x * 0.3f;   // getRotationSpeed(), Camera.cpp:129-132
+        const float pitch = mouseDelta.y * 0.3f;
+        const atx::quat orientation =
+            atx::normalize(atx::cross(atx::angleAxis(-pitch, right), atx::angleAxis(-yaw, atx::vec3(0.0f, 1.0f, 0.0f))));
+        dir = atx::rotate(orientation, dir);
+        didMove = true;
+    }
+    position[0] = pos.x; position[1] = pos.y; position[2] = pos.z;
+    direction[0] = dir.x; direction[1] = dir.y; direction[2] = dir.z;
+    if (moved)
+        *moved = didMove ? 1 : 0;
+    return ATX_OK;
+}
+
 } // extern "C"

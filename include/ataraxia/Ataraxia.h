@@ -23,6 +23,7 @@
 #include "Math.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -157,6 +158,15 @@ private:
 };
 
 // ---- Camera: Camera.h:14-88, Camera.cpp ----------------------------------------------------------
+// What Camera::onUpdate asks the window for (Core/include/input/Input.h:11-16) as plain data, so camera motion
+// can be scripted without GLFW: the six keys the camera reads, the cursor position, the right mouse button.
+struct InputState
+{
+    bool W = false, A = false, S = false, D = false, Q = false, E = false;
+    bool rightButton = false;
+    vec2 mouse{ 0.0f, 0.0f };
+};
+
 class Camera
 {
 public:
@@ -168,6 +178,26 @@ public:
     {
         UpdateViewMatrix();
         UpdateProjectionMatrix();
+    }
+
+    // Camera::onUpdate (Camera.cpp:30-108): W/S, A/D, Q/E at speed 5 and mouse look at rotation speed 0.3 while the
+    // right button is held; returns whether the camera moved. Arithmetic in the library, in glm's order.
+    bool onUpdate(float dt, const InputState& input = InputState())
+    {
+        atx_camera_input in{};
+        const auto bit = [](bool held, uint32_t key) { return held ? key : 0u; };
+        in.keys = bit(input.W, ATX_KEY_W) | bit(input.S, ATX_KEY_S) | bit(input.A, ATX_KEY_A) | bit(input.D, ATX_KEY_D) |
+                  bit(input.Q, ATX_KEY_Q) | bit(input.E, ATX_KEY_E);
+        in.right_button = input.rightButton ? 1u : 0u;
+        in.mouse_x = input.mouse.x;
+        in.mouse_y = input.mouse.y;
+        int moved = 0;
+        atx_host_camera_update(&m_position.x, &m_direction.x, &m_lastMousePos.x, &in, dt, &moved);
+        if (moved)
+            m_viewDirty = true;
+        if (m_viewDirty && input.rightButton) // :101-105 (not reached when the button is up, :36-40)
+            UpdateViewMatrix();
+        return moved != 0;
     }
 
     // Camera.cpp:110-127, including the early return that leaves a 1600x900 camera without a ray table (quirk Q-cam)
@@ -243,6 +273,7 @@ private:
     mat4 m_inverseViewMatrix{ 1.0f };
     vec3 m_position{ 0.0f };
     vec3 m_direction{ 0.0f };
+    vec2 m_lastMousePos{ 0.0f }; // Camera.h:83
     mutable std::vector<vec3> m_rayDirection;
     mutable bool m_raysValid = false;
     float m_fov = 45.0f;
@@ -621,4 +652,116 @@ inline Scene importScene(const std::string& filename) // Utils.cpp:175-187: a mi
     return deserializeScene(Json::parse(ss.str()));
 }
 } // namespace Utils
+
+// ---- Ataraxia: the application layer of Engine/src/main.cpp:8-283, without the window ------------------
+// What the application does AROUND Renderer::Render: camera motion resets the accumulation (main.cpp:22-32),
+// Render() = onResize + camera.Resize + Renderer::Render with the wall-clock "Last Render Time" (:211-220),
+// scene import/export (:196-209), and the UI widgets of onGuiRender (:34-176) as methods with the widget's own
+// reset behaviour: node, sphere and camera edits call resetFrameIndex(); material, light, "Sky Light" and
+// "Ray Depth" edits do not, and since the scene is only re-uploaded when frameIndex == 1 (Renderer.cu:175-179)
+// material and light edits stay invisible until the next reset. eagerEdits = true resets on those too.
+class Ataraxia
+{
+public:
+    explicit Ataraxia(int device = 0, bool eagerEdits = false) : m_renderer(device), m_camera(45.0f, 0.1f, 100.0f), m_eagerEdits(eagerEdits)
+    {
+        m_scene.camera = m_camera;
+        m_scene.settings = m_renderer.getSettings();
+        initializeScene();
+    }
+
+    void onUpdate(float ts, const InputState& input = InputState()) // main.cpp:22-32
+    {
+        if (m_camera.onUpdate(ts, input))
+        {
+            m_renderer.resetFrameIndex();
+            m_scene.camera = m_camera;
+            m_scene.settings = m_renderer.getSettings();
+        }
+        m_scene.rootNode->updateGlobalTransform();
+    }
+    void setViewport(uint32_t width, uint32_t height) { m_viewportWidth = width; m_viewportHeight = height; } // main.cpp:181-182
+    void Render(uint32_t frames = 1) // main.cpp:211-220
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        m_renderer.onResize(m_viewportWidth, m_viewportHeight);
+        m_camera.Resize(m_viewportWidth, m_viewportHeight);
+        m_renderer.Render(m_camera, m_scene, frames);
+        m_lastRenderTime = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    void ImportScene(const std::string& path = "scene.json") // main.cpp:196-202
+    {
+        m_scene = Utils::importScene(path);
+        m_camera = m_scene.camera;
+        m_renderer.setSettings(m_scene.settings);
+        m_renderer.resetFrameIndex();
+    }
+    void ExportScene(const std::string& path = "scene.json") // main.cpp:204-209
+    {
+        m_scene.camera = m_camera;
+        m_scene.settings = m_renderer.getSettings();
+        Utils::exportScene(m_scene, path);
+    }
+    Renderer& GetRenderer() { return m_renderer; }
+    Scene& GetScene() { return m_scene; }
+    Camera& GetCamera() { return m_camera; }
+    void SetScene(const Scene& scene) { m_scene = scene; }
+    float lastRenderTimeMs() const { return m_lastRenderTime; }
+
+    // "Settings" window (main.cpp:38-66)
+    void setAccumulation(bool on) { Settings s = m_renderer.getSettings(); s.accumulation = on; m_renderer.setSettings(s); }
+    void resetFrameIndex() { m_renderer.resetFrameIndex(); }
+    void setSkyLight(bool on) { Settings s = m_renderer.getSettings(); s.skyLight = on; m_renderer.setSettings(s); edited(); }
+    void setMaxBounces(int n) { Settings s = m_renderer.getSettings(); s.maxBounces = std::max(1, std::min(500, n)); m_renderer.setSettings(s); edited(); }
+    void setFov(float fov)
+    {
+        m_camera = Camera(fov, 0.1f, 100.0f, m_camera.getPosition(), m_camera.getDirection());
+        m_scene.camera = m_camera;
+        m_renderer.resetFrameIndex();
+    }
+    void resetCamera()
+    {
+        m_camera = Camera(45.0f, 0.1f, 100.0f);
+        m_scene.camera = m_camera;
+        m_renderer.resetFrameIndex();
+    }
+    // "Hierarchy" window (main.cpp:75-143) and the "Add" menu (:292-300)
+    void setNodePosition(SceneNode& node, const vec3& p) { node.setPosition(p); m_renderer.resetFrameIndex(); }
+    void setNodeRotation(SceneNode& node, const quat& q) { node.setRotation(q); m_renderer.resetFrameIndex(); }
+    void setNodeScale(SceneNode& node, const vec3& s) { node.setScale(s); m_renderer.resetFrameIndex(); }
+    void removeNode(const std::shared_ptr<SceneNode>& node) { m_scene.rootNode->removeChild(node); m_renderer.resetFrameIndex(); }
+    void setSphereCenter(SceneNode& node, size_t i, const vec3& c) { const_cast<Sphere&>(node.getSpheres()[i]).center = c; m_renderer.resetFrameIndex(); }
+    void setSphereRadius(SceneNode& node, size_t i, float r) { const_cast<Sphere&>(node.getSpheres()[i]).radius = r; m_renderer.resetFrameIndex(); }
+    void setSphereMaterial(SceneNode& node, size_t i, int m) { const_cast<Sphere&>(node.getSpheres()[i]).id = m; m_renderer.resetFrameIndex(); }
+    void addSphere() { m_scene.rootNode->addSphere(Sphere(vec3(0.0f), 1.0f, 0)); edited(); }
+    // "Material settings" / "Light settings" (main.cpp:145-176): edit through GetScene(), then
+    void materialOrLightEdited() { edited(); }
+
+private:
+    void edited() { if (m_eagerEdits) m_renderer.resetFrameIndex(); }
+    void initializeScene() // main.cpp:234-265
+    {
+        std::shared_ptr<SceneNode> root = m_scene.rootNode;
+        root->addSphere(Sphere(vec3(0.0f, 0.0f, 0.0f), 1.0f, 0));
+        auto childNode1 = std::make_shared<SceneNode>("ChildNode1");
+        childNode1->setPosition(vec3(2.0f, 0.0f, 0.0f));
+        childNode1->addSphere(Sphere(vec3(0.0f, 0.0f, 0.0f), 1.0f, 1));
+        root->addChild(childNode1);
+        auto grandChildNode = std::make_shared<SceneNode>("GrandChildNode");
+        grandChildNode->setPosition(vec3(0.0f, 2.0f, 0.0f));
+        grandChildNode->addSphere(Sphere(vec3(0.0f, 0.0f, 0.0f), 1.0f, 2));
+        childNode1->addChild(grandChildNode);
+        m_scene.materials.push_back(Material(vec3(1.022f, 0.782f, 0.344f), 1.0f, 0.0f, vec3(0.0f), 0.0f, 0));
+        m_scene.materials.push_back(Material(vec3(1.0f, 0.0f, 0.0f), 0.3f, 0.0f, vec3(0.0f), 0.0f, 1));
+        m_scene.materials.push_back(Material(vec3(0.972f, 0.960f, 0.915f), 0.25f, 1.0f, vec3(0.0f), 0.0f, 2));
+        m_scene.lights.push_back(Light(vec3(10.0f, 10.0f, 0.0f), vec3(1.0f), 1.0f));
+    }
+
+    Scene m_scene;
+    Renderer m_renderer;
+    Camera m_camera;
+    uint32_t m_viewportWidth = 0, m_viewportHeight = 0;
+    float m_lastRenderTime = 0.0f;
+    bool m_eagerEdits = false;
+};
 } // namespace ataraxia

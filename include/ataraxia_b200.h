@@ -276,6 +276,23 @@ ATX_API atx_status atx_host_mat4_mul(const float a[16], const float b[16], float
 /* One sphere of Renderer::traverseSceneGraph, Renderer.cu:77-88. */
 ATX_API atx_status atx_host_transform_sphere(const float global[16], const atx_sphere* in, atx_sphere* out);
 
+/* Camera::onUpdate, Camera.cpp:30-108, with the GLFW queries (Core/src/input/Input.cpp:9-35) replaced
+ * by an explicit input record, so that camera motion can be scripted without a window. keys is a
+ * bit set of the six keys the camera reads; mouse_x/mouse_y is the cursor position
+ * (Input::GetMousePosition), right_button whether MouseButton::Right is held. Updates position,
+ * direction and last_mouse in place exactly as the reference does (same glm evaluation order: the
+ * delta is taken and last_mouse advanced even when the button is up, then W/S, A/D, Q/E at speed 5,
+ * then the yaw/pitch quaternion at rotation speed 0.3) and reports what onUpdate returns in *moved.
+ * The caller rebuilds the view matrix when *moved is set (Camera.cpp:101-105). */
+typedef struct atx_camera_input {
+    uint32_t keys;          /* ATX_KEY_* bits */
+    uint32_t right_button;  /* non-zero: held */
+    float mouse_x, mouse_y;
+} atx_camera_input;
+enum { ATX_KEY_W = 1, ATX_KEY_S = 2, ATX_KEY_A = 4, ATX_KEY_D = 8, ATX_KEY_Q = 16, ATX_KEY_E = 32 };
+ATX_API atx_status atx_host_camera_update(float position[3], float direction[3], float last_mouse[2],
+                                          const atx_camera_input* input, float dt, int* moved);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,10 @@ def _f32(v, n):
     return a
 
 
+CAMERA_STEP_DTYPE = np.dtype([("dt", np.float32), ("mouse_x", np.float32), ("mouse_y", np.float32), ("keys", np.uint32),
+                              ("right", np.uint32)])
+
+
 class _CpuOracle:
     prefix = ""
     path: Path
@@ -185,6 +189,22 @@ class ReferenceCpu(_CpuOracle):
         if rc != 0:
             raise RuntimeError("reference Camera::Resize built no ray table (1600x900 quirk)")
         return rays, ip, iv
+
+    def camera_walk(self, pos, direction, fov, near, far, W, H, steps):
+        """The reference's Camera::onUpdate (Camera.cpp:30-108) driven by scripted input. steps: array of
+        CAMERA_STEP_DTYPE (dt, mouse_x, mouse_y, keys [W=1 S=2 A=4 D=8 Q=16 E=32], right). Returns per-step
+        (positions, directions, inverse view matrices, moved flags) and the final ray table."""
+        steps = np.ascontiguousarray(steps, CAMERA_STEP_DTYPE)
+        n = len(steps)
+        op, od = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        oiv, om = np.empty((n, 16), np.float32), np.empty(n, np.int32)
+        rays = np.empty((H, W, 3), np.float32)
+        fn = self.lib.refcpu_camera_walk
+        fn.restype = C.c_int
+        fn.argtypes = [_fp, _fp, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p,
+                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        fn(_f(_f32(pos, 3)), _f(_f32(direction, 3)), fov, near, far, W, H, _p(steps), n, _p(op), _p(od), _p(oiv), _p(om), _p(rays))
+        return op, od, oiv, om.astype(bool), rays
 
     def load_scene(self, path):
         """Utils::importScene + traverseSceneGraph: (spheres, materials, lights, info dict)."""

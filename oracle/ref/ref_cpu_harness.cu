@@ -101,6 +101,37 @@ REF_API int refcpu_camera(const float pos[3], const float dir[3], float fov, flo
     return 0;
 }
 
+// Camera::onUpdate (Camera.cpp:30-108) driven by a scripted input record (input_stub.cpp): one step per
+// entry of `steps` = (dt, mouseX, mouseY, keyBits, rightButton) with keyBits W=1 S=2 A=4 D=8 Q=16 E=32.
+// Outputs per step: position, direction, inverse view matrix, and what onUpdate returned.
+extern "C" void refinput_set(const uint16_t* keyCodes, int nKeys, int rightButton, float mouseX, float mouseY);
+struct RefCameraStep { float dt, mouseX, mouseY; uint32_t keys, right; };
+REF_API int refcpu_camera_walk(const float pos[3], const float dir[3], float fov, float nearClip, float farClip, uint32_t W,
+                               uint32_t H, const RefCameraStep* steps, int nSteps, float* outPos, float* outDir,
+                               float* outInvView, int* outMoved, float* finalRays)
+{
+    Camera cam(fov, nearClip, farClip, glm::vec3(pos[0], pos[1], pos[2]), glm::vec3(dir[0], dir[1], dir[2]));
+    cam.Resize(W, H);
+    static const uint16_t codes[6] = { 87, 83, 65, 68, 81, 69 }; // W S A D Q E (KeyCodes.h)
+    for (int i = 0; i < nSteps; i++)
+    {
+        uint16_t held[6];
+        int n = 0;
+        for (int k = 0; k < 6; k++)
+            if (steps[i].keys & (1u << k)) held[n++] = codes[k];
+        refinput_set(held, n, static_cast<int>(steps[i].right), steps[i].mouseX, steps[i].mouseY);
+        outMoved[i] = cam.onUpdate(steps[i].dt) ? 1 : 0;
+        std::memcpy(outPos + 3 * i, &cam.getPosition(), 12);
+        std::memcpy(outDir + 3 * i, &cam.getDirection(), 12);
+        std::memcpy(outInvView + 16 * i, &cam.getInverseViewMatrix(), 64);
+    }
+    refinput_set(nullptr, 0, 0, 0.0f, 0.0f);
+    const auto& table = cam.getRayDirection();
+    if (finalRays && table.size() == static_cast<size_t>(W) * H)
+        std::memcpy(finalRays, table.data(), table.size() * sizeof(glm::vec3));
+    return 0;
+}
+
 REF_API void refcpu_primary_hits(const void* spheres, uint32_t nS, const float origin[3], const float* dirs, uint32_t W,
                                  uint32_t H, int32_t* out, int threads)
 {

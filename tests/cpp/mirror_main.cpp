@@ -3,6 +3,8 @@
 // camera protocol (SURVEY.md §8 Q-cam). Driven by tests/test_cpp_mirror.py.
 //   mirror_main cpu <scene.json> <export.json>        -> prints flattened spheres, matrices, rays as JSON
 //   mirror_main gpu <scene.json> W H bounces sky frames <out.bin>  -> hits(int32) acc1(f32) accK(f32) rgbaK(u32)
+//   mirror_main walk <steps.bin> <out.bin> px py pz dx dy dz fov   -> scripted Camera::onUpdate, per-step camera state
+//   mirror_main app <scene.json> <out.bin>                          -> the Ataraxia layer: frame-index behaviour of edits
 #include <ataraxia/Ataraxia.h>
 #include <cstdio>
 #include <cstdlib>
@@ -18,11 +20,88 @@ static void printMat(const char* name, const mat4& m, bool last = false)
     std::printf("]%s\n", last ? "" : ",");
 }
 
+// scripted Camera::onUpdate: steps file = records of (dt, mouseX, mouseY: f32; keys [W=1 S=2 A=4 D=8 Q=16 E=32], right: u32);
+// output file = per step position(3) direction(3) inverseView(16) moved(1, as float)
+static int cameraWalk(const char* stepsPath, const char* outPath, const float* start)
+{
+    struct Step { float dt, mx, my; uint32_t keys, right; };
+    FILE* f = std::fopen(stepsPath, "rb");
+    if (!f)
+        return 3;
+    std::vector<Step> steps;
+    Step st;
+    while (std::fread(&st, sizeof(st), 1, f) == 1)
+        steps.push_back(st);
+    std::fclose(f);
+    Camera cam(start[6], 0.1f, 100.0f, vec3(start[0], start[1], start[2]), vec3(start[3], start[4], start[5]));
+    cam.Resize(48, 27);
+    FILE* o = std::fopen(outPath, "wb");
+    if (!o)
+        return 3;
+    for (const Step& s : steps)
+    {
+        InputState in;
+        in.W = s.keys & 1u; in.S = s.keys & 2u; in.A = s.keys & 4u; in.D = s.keys & 8u; in.Q = s.keys & 16u; in.E = s.keys & 32u;
+        in.rightButton = s.right != 0;
+        in.mouse = vec2(s.mx, s.my);
+        const float moved = cam.onUpdate(s.dt, in) ? 1.0f : 0.0f;
+        std::fwrite(&cam.getPosition().x, 4, 3, o);
+        std::fwrite(&cam.getDirection().x, 4, 3, o);
+        std::fwrite(&cam.getInverseViewMatrix()[0].x, 4, 16, o);
+        std::fwrite(&moved, 4, 1, o);
+    }
+    const auto& rays = cam.getRayDirection();
+    std::fwrite(&rays[0].x, 4, rays.size() * 3, o);
+    std::fclose(o);
+    return 0;
+}
+
+// the application layer without the window (main.cpp:8-283): frame-index behaviour of camera motion and UI edits
+static int appSession(const char* scenePath, const char* outPath)
+{
+    Ataraxia app;
+    app.setViewport(64, 36);
+    app.Render();                                   // default scene of initializeScene()
+    const uint32_t f0 = app.GetRenderer().frameIndex();       // 2
+    app.onUpdate(0.016f);                           // no input: nothing moves
+    app.Render(3);
+    const uint32_t f1 = app.GetRenderer().frameIndex();       // 5
+    InputState in;
+    in.rightButton = true; in.W = true; in.mouse = vec2(12.0f, -7.0f);
+    app.onUpdate(0.016f, in);                       // camera moved: accumulation restarts
+    const uint32_t f2 = app.GetRenderer().frameIndex();       // 1
+    app.Render(2);
+    app.GetScene().materials[0].albedo = vec3(0.1f, 0.9f, 0.1f);
+    app.materialOrLightEdited();                    // reference behaviour: no reset
+    const uint32_t f3 = app.GetRenderer().frameIndex();       // 3
+    app.setNodePosition(*app.GetScene().rootNode->getChildren()[0], vec3(2.5f, 0.0f, 0.0f));
+    const uint32_t f4 = app.GetRenderer().frameIndex();       // 1
+    app.ImportScene(scenePath);
+    app.Render(2);
+    const std::vector<float> acc = app.GetRenderer().getAccumulation();
+    FILE* o = std::fopen(outPath, "wb");
+    if (!o)
+        return 3;
+    std::fwrite(acc.data(), 4, acc.size(), o);
+    std::fclose(o);
+    std::printf("%u %u %u %u %u %u %.3f\n", f0, f1, f2, f3, f4, app.GetRenderer().frameIndex(), app.lastRenderTimeMs() >= 0.0f ? 1.0 : 0.0);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3)
         return 2;
     const std::string mode = argv[1];
+    if (mode == "walk" && argc >= 11)
+    {
+        float start[7];
+        for (int i = 0; i < 7; i++)
+            start[i] = static_cast<float>(std::atof(argv[4 + i]));
+        return cameraWalk(argv[2], argv[3], start);
+    }
+    if (mode == "app" && argc >= 4)
+        return appSession(argv[2], argv[3]);
     Scene scene = Utils::importScene(argv[2]);
     if (mode == "cpu")
     {

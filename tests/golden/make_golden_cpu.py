@@ -68,6 +68,23 @@ def main():
     hits = ref.primary_hits(s_, info["position"], rays)
     out["c1_hit_histogram"] = np.array([(hits == k).sum() for k in (-1, 0, 1, 2)], np.int64)
     out["c1_center_ray"] = rays[360, 640]
+    # Camera::onUpdate (Camera.cpp:30-108) under a scripted input sequence: 160 steps of keys, mouse motion and
+    # right-button state (fixed seed), starting from the sample scene's camera
+    from oracle.bindings import CAMERA_STEP_DTYPE
+    rng = np.random.default_rng(0xCA3E7A)
+    n = 160
+    steps = np.zeros(n, CAMERA_STEP_DTYPE)
+    steps["dt"] = rng.uniform(0.001, 0.05, n).astype(np.float32)
+    steps["mouse_x"] = np.cumsum(rng.normal(0, 25, n)).astype(np.float32)
+    steps["mouse_y"] = np.cumsum(rng.normal(0, 15, n)).astype(np.float32)
+    steps["keys"] = rng.integers(0, 64, n)
+    steps["right"] = rng.random(n) < 0.8
+    steps["mouse_x"][40:44] = steps["mouse_x"][39]          # a few steps without mouse motion
+    steps["mouse_y"][40:44] = steps["mouse_y"][39]
+    steps["keys"][40:42] = 0                                # ... and without keys: onUpdate returns false
+    op, od, oiv, om, wrays = ref.camera_walk(info["position"], info["direction"], info["fov"], 0.1, 100.0, 48, 27, steps)
+    out["walk_steps"] = steps.view(np.uint8)
+    out["walk_pos"], out["walk_dir"], out["walk_invview"], out["walk_moved"], out["walk_rays"] = op, od, oiv, om, wrays
     np.savez_compressed(G / "cpu_golden.npz", **out)
     print("wrote", G / "cpu_golden.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
 

@@ -430,6 +430,75 @@ def test_settings_and_edge_cases(atx, port):
     r.close(); r2.close()
 
 
+def test_application_layer_semantics(atx):
+    """The `Ataraxia` layer of main.cpp without the window: which edits restart the
+    accumulation, when an edit becomes visible (the scene is only re-uploaded at frameIndex == 1,
+    Renderer.cu:175-179), and scripted camera motion."""
+    app = atx.Ataraxia()
+    r = app.GetRenderer()
+    app.setViewport(96, 54)
+    app.setMaxBounces(6)
+    app.Render(); app.Render(2)
+    assert r.frameIndex() == 4 and (r.getAccumulation()[..., 3] == 3).all()
+    app.onUpdate(0.016)                                             # no input: nothing moves, nothing resets
+    assert r.frameIndex() == 4
+    # a material edit does not reset and is not uploaded: the next frames continue with the OLD material
+    app.editMaterial(0, albedo=(0.1, 0.9, 0.1))
+    assert r.frameIndex() == 4
+    app.Render(2)
+    stale = r.getAccumulation()
+    ref = atx.Ataraxia(); ref.setViewport(96, 54); ref.setMaxBounces(6); ref.Render(5)
+    assert (bits(stale) == bits(ref.GetRenderer().getAccumulation())).all()
+    # ... until the next reset: then it is
+    app.resetFrameIndex(); app.Render(5)
+    fresh = r.getAccumulation()
+    assert not (bits(fresh) == bits(stale)).all()
+    ref.editMaterial(0, albedo=(0.1, 0.9, 0.1)); ref.resetFrameIndex(); ref.Render(5)
+    assert (bits(fresh) == bits(ref.GetRenderer().getAccumulation())).all()
+    ref.close()
+    # node / sphere edits reset at once (main.cpp:89-126)
+    child = app.GetScene().rootNode.getChildren()[0]
+    app.setNodePosition(child, (2.5, 0.0, 0.0)); assert r.frameIndex() == 1
+    app.Render(); app.setSphereRadius(child, 0, 0.7); assert r.frameIndex() == 1
+    app.Render(); app.setSphereMaterial(child, 0, 2); assert r.frameIndex() == 1
+    app.Render(); app.setFov(60.0); assert r.frameIndex() == 1 and app.m_camera.getFov() == 60.0
+    # camera motion (right button held) resets; with the button up it does not
+    app.Render(3)
+    app.onUpdate(0.016, atx.InputState("W", (5.0, 5.0), False)); assert r.frameIndex() == 4
+    app.onUpdate(0.016, atx.InputState("W", (9.0, 2.0), True)); assert r.frameIndex() == 1
+    assert (app.GetScene().camera.getPosition() == app.m_camera.getPosition()).all()
+    # scripted path: every moving step restarts the accumulation, the still ones add up
+    script = [(0.016, atx.InputState("D", (9.0 + 3 * i, 2.0), True)) for i in range(3)] + [(0.016, atx.InputState("", (15.0, 2.0), True))] * 2
+    assert app.playCameraPath(script, frames_per_step=2) == [3, 3, 3, 5, 7]
+    # eager mode: material and light edits reset too
+    eager = atx.Ataraxia(eagerEdits=True); eager.setViewport(32, 18); eager.Render(2)
+    eager.editLight(0, intensity=2.0); assert eager.GetRenderer().frameIndex() == 1
+    eager.close()
+    # accumulation off: frameIndex stays 1, so every frame re-uploads and an edit shows at once (Renderer.cu:245-248)
+    app.setAccumulation(False); app.resetFrameIndex(); app.Render(); a = r.getAccumulation()
+    app.editLight(0, intensity=3.0); app.Render(); b = r.getAccumulation()
+    assert r.frameIndex() == 1 and not (bits(a) == bits(b)).all()
+    assert app.lastRenderTimeMs() > 0.0
+    app.close()
+
+
+def test_application_default_scene_vs_live_reference(atx, tmp_path):
+    """initializeScene() (main.cpp:234-265) exported by the layer and rendered by the unmodified reference."""
+    from oracle import bindings as ob
+    if not ob.have_ref_headless():
+        pytest.skip("oracle/_ref/ref_headless not present")
+    app = atx.Ataraxia()
+    app.setViewport(200, 120)
+    app.setMaxBounces(7); app.setSkyLight(True)
+    path = tmp_path / "default.json"
+    app.ExportScene(str(path))
+    app.Render(); app.Render(3)
+    info, ref = ob.run_ref_headless(path, 200, 120, 7, True, 4, dump_at=(4,))
+    assert (bits(app.GetRenderer().getAccumulation()) == bits(ref["acc4"])).all()
+    assert (app.GetRenderer().getImage().data == ref["rgba4"]).all()
+    app.close()
+
+
 def test_error_behaviour(atx):
     r = atx.Renderer(0)
     with pytest.raises(atx.AtxError):

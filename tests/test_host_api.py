@@ -109,6 +109,72 @@ def test_camera_quirks(built):
     assert not (c2.getInverseProjectionMatrix() == np.eye(4, dtype=np.float32).reshape(-1)).all()
 
 
+def _walk(cam, steps):
+    pos, dirs, iv, moved = [], [], [], []
+    for st in steps:
+        keys = "".join(c for b, c in enumerate("WSADQE") if (int(st["keys"]) >> b) & 1)
+        moved.append(cam.onUpdate(float(st["dt"]), atx.InputState(keys, (float(st["mouse_x"]), float(st["mouse_y"])), bool(st["right"]))))
+        pos.append(cam.getPosition().copy()); dirs.append(cam.getDirection().copy()); iv.append(cam.getInverseViewMatrix().copy())
+    return np.array(pos), np.array(dirs), np.array(iv), np.array(moved)
+
+
+def test_scripted_camera_walk_matches_reference_golden(built, gold):
+    """Camera::onUpdate (Camera.cpp:30-108) under 160 scripted input steps: position, direction, inverse view
+    matrix and the returned flag after EVERY step, and the final ray table, bit for bit against what the
+    unmodified reference produced with the same inputs (tests/golden/make_golden_cpu.py)."""
+    from oracle.bindings import CAMERA_STEP_DTYPE
+    steps = gold["walk_steps"].view(CAMERA_STEP_DTYPE)
+    cam = atx.Camera(float(gold["sample_fov"]), 0.1, 100.0, gold["sample_campos"], gold["sample_camdir"])
+    cam.Resize(48, 27)
+    pos, dirs, iv, moved = _walk(cam, steps)
+    assert (bits(pos) == bits(gold["walk_pos"])).all()
+    assert (bits(dirs) == bits(gold["walk_dir"])).all()
+    assert (bits(iv) == bits(gold["walk_invview"])).all()
+    assert (moved == gold["walk_moved"]).all() and 0 < moved.sum() < len(moved)
+    assert (bits(cam.getRayDirection()) == bits(gold["walk_rays"])).all()
+
+
+def test_scripted_camera_walk_matches_live_reference(built, refcpu):
+    """The same against the reference library itself on a fresh random script (only where it was built)."""
+    from oracle.bindings import CAMERA_STEP_DTYPE
+    rng = np.random.default_rng(77)
+    n = 300
+    steps = np.zeros(n, CAMERA_STEP_DTYPE)
+    steps["dt"] = rng.uniform(0.0, 0.1, n)
+    steps["mouse_x"] = np.cumsum(rng.normal(0, 40, n)); steps["mouse_y"] = np.cumsum(rng.normal(0, 40, n))
+    steps["keys"] = rng.integers(0, 64, n); steps["right"] = rng.random(n) < 0.7
+    start_p, start_d = np.array([3.0, 1.0, -4.0], np.float32), np.array([-0.6, -0.1, 0.79], np.float32)
+    op, od, oiv, om, rays = refcpu.camera_walk(start_p, start_d, 60.0, 0.1, 100.0, 40, 30, steps)
+    cam = atx.Camera(60.0, 0.1, 100.0, start_p, start_d)
+    cam.Resize(40, 30)
+    pos, dirs, iv, moved = _walk(cam, steps)
+    assert (bits(pos) == bits(op)).all() and (bits(dirs) == bits(od)).all() and (bits(iv) == bits(oiv)).all()
+    assert (moved == om).all()
+    assert (bits(cam.getRayDirection()) == bits(rays)).all()
+
+
+def test_camera_update_semantics(built):
+    cam = atx.Camera(45.0, 0.1, 100.0)
+    p0, d0 = cam.getPosition().copy(), cam.getDirection().copy()
+    # button up: nothing moves, but the mouse position is remembered (Camera.cpp:33-40)
+    assert cam.onUpdate(0.1, atx.InputState("W", (50.0, 20.0), False)) is False
+    assert (cam.getPosition() == p0).all() and cam.m_lastMousePos.tolist() == [50.0, 20.0]
+    # button down, same mouse position, W: forward by speed * dt = 0.5 along the direction
+    assert cam.onUpdate(0.1, atx.InputState("W", (50.0, 20.0), True)) is True
+    assert np.allclose(cam.getPosition(), p0 + d0 * 0.5) and (cam.getDirection() == d0).all()
+    # W wins over S, A over D, Q over E (else-if chains, Camera.cpp:51-85)
+    c2 = atx.Camera(45.0, 0.1, 100.0)
+    c2.onUpdate(0.1, atx.InputState("WSADQE", (0.0, 0.0), True))
+    c3 = atx.Camera(45.0, 0.1, 100.0)
+    c3.onUpdate(0.1, atx.InputState("WAQ", (0.0, 0.0), True))
+    assert (bits(c2.getPosition()) == bits(c3.getPosition())).all()
+    # mouse motion alone rotates and keeps the position
+    c4 = atx.Camera(45.0, 0.1, 100.0)
+    assert c4.onUpdate(0.016, atx.InputState("", (30.0, -10.0), True)) is True
+    assert (c4.getPosition() == p0).all() and not (c4.getDirection() == d0).all()
+    assert abs(np.linalg.norm(c4.getDirection()) - 1.0) < 1e-5
+
+
 # ---- scene graph -------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,file", [("sample", "sample_scene.json"), ("small", "small_scene.json")])
 def test_import_and_flatten_match_reference(built, gold, name, file):
