@@ -425,6 +425,12 @@ class Renderer:
         check(_capi.lib().atx_last_render_ms(self._h, C.byref(v)))
         return v.value
 
+    def lastMegaKind(self) -> int:
+        """Megakernel form of the last launch (MEGA_WHILE_WHILE / MEGA_PAIR / MEGA_WARP_QUEUE)."""
+        v = C.c_int()
+        check(_capi.lib().atx_last_mega_kind(self._h, C.byref(v)))
+        return v.value
+
     def eventRecord(self, slot: int): check(_capi.lib().atx_event_record(self._h, slot))
 
     def eventElapsedMs(self, begin: int, end: int) -> float:

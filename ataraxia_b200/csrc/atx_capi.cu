@@ -140,7 +140,8 @@ struct atx_renderer
     uint32_t frameIndex = 1;
     uint32_t lastFrame = 1;     // frameIndex of the last rendered frame (display divisor)
     uint32_t chunkOverride = 0; // tuning: force the shared-memory chunk size (spheres)
-    int megaKind = 0;           // tuning: 0 = by sphere count, 1 = while-while, 2 = two-slot packed
+    int megaKind = 0;           // tuning: 0 = by sphere count and frames per launch, 1 = while-while, 2 = two-slot packed, 3 = warp-queue
+    int lastKind = 0;           // form the last megakernel launch used
     uint32_t parkThreshold = 8;  // tuning: parked hits per warp that trigger the bounce phase (while-while form)
     uint32_t claimThreshold = 0; // tuning: idle lanes per warp that trigger a batched pixel claim (0 = per form)
     uint64_t launches = 0;
@@ -453,6 +454,7 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.rgbaDivisor = rgbaDivisor;
     if (variant == ATX_VARIANT_WAVEFRONT)
     {
+        h->lastKind = 0;
         if (h->maxBounces > atx_launch::kWavefrontMaxBounces)
             return fail(ATX_ERR_INVALID, "the wavefront variant supports maxBounces <= %d", atx_launch::kWavefrontMaxBounces);
         if (static_cast<size_t>(h->nS) * sizeof(float4) > static_cast<size_t>(atx_launch::kMaxSmemBytes))
@@ -481,6 +483,7 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     const int formKind = atx_launch::mega_kind(p, h->megaKind);
     p.claimThreshold = h->claimThreshold ? h->claimThreshold
                                          : (formKind == atx_launch::kMegaWhileWhile ? 32u : formKind == atx_launch::kMegaWarpQueue ? 3u : 2u);
+    h->lastKind = formKind;
     ATX_CUDA(cudaMemsetAsync(h->dPool, 0, sizeof(uint32_t), h->stream));
     ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->smCount, h->stream));
     h->launches++;
@@ -607,6 +610,14 @@ atx_status atx_last_render_ms(atx_handle h, float* out_ms)
         return fail(ATX_ERR_INVALID, "nothing rendered yet");
     ATX_CUDA(cudaEventSynchronize(h->evStop));
     ATX_CUDA(cudaEventElapsedTime(out_ms, h->evStart, h->evStop));
+    return ATX_OK;
+}
+
+atx_status atx_last_mega_kind(atx_handle h, int* out)
+{
+    if (!h || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    *out = h->lastKind;
     return ATX_OK;
 }
 

@@ -44,12 +44,14 @@ WORKLOADS = {
     "c3": ("synthetic 256 spheres 16 lights 3840x2160 256spp 8 bounces", 3840, 2160, 256, 8),
     "c4": ("synthetic 4096 spheres 3840x2160 64spp 8 bounces", 3840, 2160, 64, 8),
     "c1": ("sample-scene-data/scene.json 1280x720 1spp 5 bounces", 1280, 720, 1, 5),
+    # config 5: the TOTAL spp is fixed and split across the ranks (strong scaling), float4 buffers NCCL-summed
+    "c5": ("sample-scene-data/scene.json 7680x4320 16384spp split across the GPUs, 8 bounces", 7680, 4320, 16384, 8),
     "c16k": ("synthetic 16384 spheres (chunked TMA staging) 1920x1080 16spp 8 bounces", 1920, 1080, 16, 8),
 }
 
 
 def load_scene(atx, name):
-    if name in ("c1", "c2"):
+    if name in ("c1", "c2", "c5"):
         return atx.Utils.importScene(str(ROOT / "tests" / "golden" / "sample_scene.json"))
     if name == "c16k":
         return atx.synthetic.stress16k()
@@ -106,7 +108,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_arm(workload, steps, warmup, threads=0, target_seconds=4.0):
+def cpu_reference_arm(workload, steps, warmup, threads=0, target_seconds=10.0):
     """The reference's per-pixel path on the host cores: oracle/_ref/libref_cpu.so (reference sources
     compiled host-side) when present, else the oracle port. Bounded sample of the workload per step."""
     import ataraxia_b200 as atx
@@ -170,6 +172,47 @@ def ref_cuda_baseline(workload, frames=24):
             "note": "end-to-end Render() wall time per 1-spp frame (host ray-table upload + sync + RGBA8 read-back included, as the app runs it)"}
 
 
+def secondary_workload(atx, name, local_rank, flush, steps=2, warmup=3):
+    """One of the other BASELINE configs on the same GPU, device-timed like the headline: reported next to it
+    (the headline scene has 3 spheres, so its FP32 fraction is small by construction; configs 3 and 4 are the
+    ones the sphere loop dominates)."""
+    import torch
+    desc, W, H, spp, bounces = WORKLOADS[name]
+    scene = load_scene(atx, name)
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    r = atx.Renderer(local_rank)
+    r.setSettings(atx.Settings(True, False, bounces))
+    r.variant = atx.VARIANT_MEGAKERNEL
+    r.onResize(W, H)
+    cam.Resize(W, H)
+    spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
+    r.uploadArrays(spheres, atx.pack_materials(scene.materials), atx.pack_lights(scene.lights))
+    r.setCamera(cam)
+    for _ in range(warmup):
+        r.renderFrames(1, max(1, spp // 8), 1, zero_first=True)
+    r.sync()
+    r.resetCounters()
+    ms = []
+    for _ in range(steps):
+        flush.fill_(0)
+        torch.cuda.synchronize()
+        r.eventRecord(0)
+        r.renderFrames(1, spp, 1, zero_first=True)
+        r.eventRecord(1)
+        ms.append(r.eventElapsedMs(0, 1))
+    c = r.counters()
+    total = sum(ms) * 1e-3
+    flops = FLOP_PER_TEST * float(c.sphere_tests_executed) + FLOP_PER_RAY * float(c.rays_traced)
+    out = {"workload": desc, "spheres": int(len(spheres)), "lights": int(len(scene.lights)), "steps": steps,
+           "warmup": f"{warmup} x {max(1, spp // 8)} spp", "ms_per_step": sum(ms) / steps,
+           "form": {1: "while-while", 2: "two-slot packed", 3: "warp-queue"}.get(r.lastMegaKind(), "?"),
+           "value": float(c.paths) / total / 1e6, "unit": "Mpaths/s", "grays_per_s": float(c.rays) / total / 1e9,
+           "roofline": {"bound": "fp32_fma", "achieved": flops / total / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": flops / total / 1e12 / FP32_PEAK_TFLOPS}}
+    r.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,7 +224,7 @@ def main():
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference-CUDA legs")
     ap.add_argument("--variant", default="megakernel", choices=["megakernel", "wavefront", "auto"],
                     help="kernel family (bit-identical results); auto = atx_calibrate's pick")
-    ap.add_argument("--mega-kind", type=int, default=0, help="0 auto, 1 while-while, 2 two-slot packed (same results)")
+    ap.add_argument("--mega-kind", type=int, default=0, help="0 auto, 1 while-while, 2 two-slot packed, 3 warp-queue (same results)")
     ap.add_argument("--park-threshold", type=int, default=0, help="while-while form: parked hits per warp that trigger the bounce phase")
     ap.add_argument("--claim-threshold", type=int, default=0, help="idle lanes per warp that trigger a batched pixel claim")
     ap.add_argument("--chunk", type=int, default=0, help="force the shared-memory chunk size in spheres (0 = automatic)")
@@ -194,6 +237,9 @@ def main():
     desc, W, H, spp, bounces = WORKLOADS[args.workload]
     if args.spp:
         spp = args.spp
+    strong = args.workload == "c5"
+    if strong:
+        spp = max(1, spp // world)   # per-GPU share of the fixed total
 
     if args.impl == "reference":
         if rank != 0:
@@ -271,7 +317,7 @@ def main():
     dev_ms = []
     for _ in range(args.steps):
         flush.fill_(0)            # L2 flush between timed iterations (not inside the event bracket)
-        torch.cuda.synchronize()
+        barrier()                 # ranks enter the step together: the all-reduce inside it must not time their skew
         step()
         dev_ms.append(r.eventElapsedMs(0, 1))
     barrier()
@@ -338,10 +384,11 @@ def main():
         line = {
             "metric": "Mpaths/s", "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
                        "spheres": int(len(spheres)), "lights": int(len(lights)), "parallelism": f"spp-split x{world}",
-                       "l2": "flushed between steps (256 MB write)", "variant": args.variant, "mega_kind": args.mega_kind, "park_threshold": args.park_threshold, "chunk": args.chunk},
+                       "l2": "flushed between steps (256 MB write)", "variant": args.variant, "mega_kind": args.mega_kind,
+                       "form": {0: "wavefront", 1: "while-while", 2: "two-slot packed", 3: "warp-queue"}.get(r.lastMegaKind(), "?"), "park_threshold": args.park_threshold, "chunk": args.chunk},
             "calibration_ms": calibration,
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "grays_traced_per_s": rays_x / (total_ms * 1e-3) / 1e9,
@@ -362,11 +409,20 @@ def main():
                                        "peak_gbs": peaks.get("hbm_gbs")}},
         }
         if world == 1 and not args.no_baselines:
+            t_leg = time.perf_counter()
+
+            def leg(name):
+                nonlocal t_leg
+                print(f"[bench] {name}: {time.perf_counter() - t_leg:.1f} s", file=sys.stderr, flush=True)
+                t_leg = time.perf_counter()
+
             cb = cpu_reference_arm(args.workload, 1, 0)
+            leg("cpu_baseline")
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             rc = ref_cuda_baseline(args.workload)
             if rc:
                 line["ref_cuda_baseline"] = rc
+            leg("ref_cuda_baseline")
             # BASELINE metric part 2: ms/frame at 1 spp (config 1), end to end through Renderer::Render
             s1 = load_scene(atx, "c1")
             cam1 = atx.Camera(s1.camera.getFov(), 0.1, 100.0, s1.camera.getPosition(), s1.camera.getDirection())
@@ -382,6 +438,11 @@ def main():
                                          "config": WORKLOADS["c1"][0], "kernel_ms": r1.lastRenderMs(),
                                          "includes": "Render(): camera, launch, RGBA8 read-back to host"}
             r1.close()
+            leg("ms_per_frame_1spp")
+            # the other BASELINE configs on this GPU (the ones the sphere loop dominates)
+            if args.workload == "c2":
+                line["other_workloads"] = {k: secondary_workload(atx, k, local_rank, flush) for k in ("c3", "c4")}
+                leg("other_workloads")
         print(json.dumps(line))
     r.close()
     if world > 1:

@@ -196,6 +196,10 @@ ATX_API atx_status atx_last_render_ms(atx_handle h, float* out_ms);
 
 /* General-purpose device timers on the handle's stream (CUDA events), e.g. to bracket
  * render + all-reduce. slot in [0, 8). elapsed synchronises on the later event. */
+/* Megakernel form the last launch used (1 while-while, 2 two-slot packed, 3 warp-queue; 0 before any launch
+ * or after a wavefront launch): what ATX_TUNE_MEGA_KIND = 0 resolved to. */
+ATX_API atx_status atx_last_mega_kind(atx_handle h, int* out);
+
 ATX_API atx_status atx_event_record(atx_handle h, int slot);
 ATX_API atx_status atx_event_elapsed_ms(atx_handle h, int slot_begin, int slot_end, float* out_ms);
 
