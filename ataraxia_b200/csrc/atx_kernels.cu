@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 // that completes while nothing older is pending goes straight to the sum). A lane whose
 // ring is full skips G until its oldest path has come back; B runs at once with 32 queued
 // hits and earlier when stalled lanes have cost as much as a narrow B would waste.
-// Measured on config 2 (1024 frames): G runs 28.9 lanes wide, B 28.4; 24.4 ms against the
+// Measured on config 2 (1024 frames): G runs 28.9 lanes wide, B 28.4; 22.6 ms against the
 // while-while form's 31.1 ms. Shared memory (10.4 KB per warp) allows 20 warps per SM; a
 // 32-slot ring at 12 warps per SM is slower (32.5 ms), an 8-slot ring at 24 warps equal.
 // Same path_* code between traces as every other form, same frame order of the sums: the
@@ -645,6 +645,15 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 #endif
 #ifndef ATX_WQ_BOOKKEEP
 #define ATX_WQ_BOOKKEEP 7u // retire/claim check every 8th pass of the warp loop (power of two minus one; measured: every pass 25.5 ms, 4th 24.7, 8th 24.5)
+#endif
+#ifndef ATX_WQ_GUNROLL
+#define ATX_WQ_GUNROLL 1
+#endif
+#ifndef ATX_WQ_GREPEAT
+#define ATX_WQ_GREPEAT 2u // frames a lane generates per pass of the warp loop (one light; measured: 1: 23.4 ms, 2: 22.6, 3: 23.5)
+#endif
+#ifndef ATX_WQ_CONSUME
+#define ATX_WQ_CONSUME 3u // completed ring slots are added to the sums every (mask + 1)th pass (measured at one frame per pass: every pass 24.4 ms, 2nd 24.1, 4th 23.9, 8th 23.8)
 #endif
 #ifndef ATX_WQ_BFULL
 #define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
@@ -685,21 +694,23 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     unsigned long long wqStat[8] = {};
 #endif
 
-    auto trace = [&](const PathState& s, float& tmin, int& closest) {
+    auto trace_ray = [&](float ox, float oy, float oz, float dx, float dy, float dz, float& tmin, int& closest) {
         tmin = 3.402823466e+38f; // FLT_MAX
         closest = -1;
-        const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
-        trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+        const RayConst rk = ray_constants(dx, dy, dz);
+        trace_range(sphS, p.nSpheres, 0u, ox, oy, oz, dx, dy, dz, rk, tmin, closest);
         traced++;
     };
+    auto trace = [&](const PathState& s, float& tmin, int& closest) { trace_ray(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, tmin, closest); };
     // a finished path hands its sample to the pixel's ring
-    auto complete = [&](uint32_t tag, const PathState& s) {
+    auto complete3 = [&](uint32_t tag, float cr, float cg, float cb) {
         const uint32_t pl = tag & 31u, slot = tag >> 8;
-        ring[(0u * K + slot) * 32u + pl] = s.cr;
-        ring[(1u * K + slot) * 32u + pl] = s.cg;
-        ring[(2u * K + slot) * 32u + pl] = s.cb;
+        ring[(0u * K + slot) * 32u + pl] = cr;
+        ring[(1u * K + slot) * 32u + pl] = cg;
+        ring[(2u * K + slot) * 32u + pl] = cb;
         atomicOr(done + pl, 1u << slot);
     };
+    auto complete = [&](uint32_t tag, const PathState& s) { complete3(tag, s.cr, s.cg, s.cb); };
 
     // per-pixel state (lane = the pixel it owns until every frame of it is in the sum)
     bool live = false;      // owns a pixel with frames to render through G/B
@@ -797,7 +808,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
         while (true)
         {
             // ---- add completed samples in frame order ----
-            if (live && head < j)
+            if (live && head < j && (pass & ATX_WQ_CONSUME) == 0u)
             {
                 uint32_t d = done[lane];
                 while (head < j && ((d >> (head & (K - 1u))) & 1u))
@@ -901,65 +912,104 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             else if (genMask != 0u)
             {
                 // ---- G: the next frame of this lane's pixel ----
-                stallDebt += nStalled;
+                stallDebt += nStalled * (kFixedLight ? ATX_WQ_GREPEAT : 1u);
                 WQ_STAT(0, 1); WQ_STAT(1, __popc(genMask)); WQ_STAT(2, nStalled);
                 WQ_STAT(3, __popc(__ballot_sync(kFull, live && j >= p.nFrames)));
-                if (gen)
+                if (!kFixedLight)
                 {
-                    const uint32_t frame = p.firstFrame + j * p.frameStride;
-                    tag = lane | ((j & (K - 1u)) << 8);
-                    rays += raysPerStart;
-                    bool flying = false;
-                    if (!kFixedLight)
+                    if (gen)
                     {
                         // the path starts at the cached primary hit: straight to the bounce queue
-                        path_begin(s, p.cam.pos, d0, pixel, frame);
+                        tag = lane | ((j & (K - 1u)) << 8);
+                        rays += raysPerStart;
+                        path_begin(s, p.cam.pos, d0, pixel, p.firstFrame + j * p.frameStride);
                         wantPush = true;
                         hitT = tPrimary;
                         hitC = cPrimary;
+                        j++;
                     }
-                    else
+                }
+                else
+                {
+                    // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in. The path
+                    // state of this branch IS the per-pixel constants plus a seed and a direction, so it is kept in
+                    // its own registers and queued from them (no copy into a PathState)
+#if ATX_WQ_GUNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+                    for (uint32_t rep = 0u; rep < ATX_WQ_GREPEAT; rep++)
                     {
-                        // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in
-                        s.cr = c0r; s.cg = c0g; s.cb = c0b;
-                        s.seed = pixel * frame;
-                        if (!(pcg_float(s.seed) > pr0))
+                    // (several frames per pass: the pass overhead - ring consumption, ballots, the B decision - is
+                    // paid once; a further frame only while the queue is sure to take 32 more hits)
+                    const bool genNow = rep == 0u ? gen : (live && j < p.nFrames && (j - head) < K);
+                    bool hit = false;
+                    uint32_t seed = 0u;
+                    V3 nd = { 0.0f, 0.0f, 0.0f };
+                    const uint32_t gtag = lane | ((j & (K - 1u)) << 8);
+                    if (genNow)
+                    {
+                        rays += raysPerStart;
+                        seed = pixel * (p.firstFrame + j * p.frameStride);
+                        bool flying = false;
+                        if (!(pcg_float(seed) > pr0))
                         {
                             float lx, ly, lz;
-                            sample_local(ggx0, ggxT0, s.seed, lx, ly, lz);
-                            const V3 nd = frame_combine(N0, T0, B0, lx, ly, lz);
+                            sample_local(ggx0, ggxT0, seed, lx, ly, lz);
+                            nd = frame_combine(N0, T0, B0, lx, ly, lz);
                             if (1 < p.maxBounces)
                             {
-                                s.ox = o0x; s.oy = o0y; s.oz = o0z;
-                                s.dx = nd.x; s.dy = nd.y; s.dz = nd.z;
-                                s.tx = tq0x; s.ty = tq0y; s.tz = tq0z;
-                                s.bounce = 1;
-                                s.seed += 1u; // Renderer.cu:306
+                                seed += 1u; // Renderer.cu:306
                                 flying = true;
                             }
                         }
                         if (flying)
                         {
-                            trace(s, hitT, hitC);
+                            trace_ray(o0x, o0y, o0z, nd.x, nd.y, nd.z, hitT, hitC);
                             rays++;
-                            if (hitC >= 0)
-                                wantPush = true;
-                            else
-                                path_miss(p, s);
+                            hit = hitC >= 0;
                         }
-                    }
-                    if (!wantPush)
-                    {
-                        // the path is complete: straight to the sum when nothing older is pending
-                        if (head == j)
+                        if (!hit)
                         {
-                            accumulate_sample(acc, s);
-                            head++;
+                            // the path is complete: its sample is the cached color (+ the sky seen by the bounce ray,
+                            // path_miss); straight to the sum when nothing older is pending
+                            float cr = c0r, cg = c0g, cb = c0b;
+                            if (flying && p.skyLight)
+                            {
+                                cr = ffma(tq0x, 0.6f, cr);
+                                cg = ffma(tq0y, 0.7f, cg);
+                                cb = ffma(tq0z, 0.9f, cb);
+                            }
+                            if (head == j)
+                            {
+                                acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
+                                acc.w = fadd(acc.w, 1.0f);
+                                head++;
+                            }
+                            else
+                                complete3(gtag, cr, cg, cb);
                         }
-                        else
-                            complete(tag, s);
+                        j++;
                     }
-                    j++;
+                    const unsigned m = __ballot_sync(kFull, hit);
+                    if (hit)
+                    {
+                        const uint32_t e = (qHead + qCount + __popc(m & ((1u << lane) - 1u))) & (kQueueCap - 1u);
+                        qf[0u * kQueueCap + e] = o0x; qf[1u * kQueueCap + e] = o0y; qf[2u * kQueueCap + e] = o0z;
+                        qf[3u * kQueueCap + e] = nd.x; qf[4u * kQueueCap + e] = nd.y; qf[5u * kQueueCap + e] = nd.z;
+                        qf[6u * kQueueCap + e] = c0r; qf[7u * kQueueCap + e] = c0g; qf[8u * kQueueCap + e] = c0b;
+                        qf[9u * kQueueCap + e] = tq0x; qf[10u * kQueueCap + e] = tq0y; qf[11u * kQueueCap + e] = tq0z;
+                        q[12u * kQueueCap + e] = seed;
+                        q[13u * kQueueCap + e] = 1u; // bounce
+                        qf[14u * kQueueCap + e] = hitT;
+                        q[15u * kQueueCap + e] = static_cast<uint32_t>(hitC);
+                        q[16u * kQueueCap + e] = gtag;
+                    }
+                    qCount += __popc(m);
+                    if (qCount > 32u)
+                        break;
+                    }
                 }
             }
             else if (__all_sync(kFull, exhausted && !live))
