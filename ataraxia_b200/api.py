@@ -283,6 +283,24 @@ class Image:
             f.write(f"P6\n{self.m_width} {self.m_height}\n255\n".encode())
             f.write(rgb.tobytes())
 
+    def savePNG(self, path: str) -> None:
+        """The same image (RGBA8 as packed by Renderer.h:70-78, V flipped like the UI) as a PNG: 8-bit RGBA, filter
+        0 on every row, zlib stream from the standard library."""
+        import struct
+        import zlib
+        px = np.ascontiguousarray(self.data[::-1]).astype("<u4")
+        rows = px.view(np.uint8).reshape(self.m_height, self.m_width * 4)   # bytes r, g, b, a
+        raw = np.concatenate([np.zeros((self.m_height, 1), np.uint8), rows], axis=1).tobytes()
+
+        def chunk(kind: bytes, body: bytes) -> bytes:
+            return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+
+        with open(path, "wb") as f:
+            f.write(b"\x89PNG\r\n\x1a\n")
+            f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", self.m_width, self.m_height, 8, 6, 0, 0, 0)))
+            f.write(chunk(b"IDAT", zlib.compress(raw, 6)))
+            f.write(chunk(b"IEND", b""))
+
 
 def traverseSceneGraph(node: Optional[SceneNode], parentTransform=None) -> List[Sphere]:
     """Renderer::traverseSceneGraph (Renderer.cu:67-96): pre-order, world-space centres, mean-scale radii."""
@@ -446,6 +464,16 @@ class Renderer:
             out = np.empty((self.m_height, self.m_width, 4), np.float32)
         check(_capi.lib().atx_read_accum(self._h, vptr(out)))
         return out
+
+    def saveAccumulationPFM(self, path: str) -> None:
+        """Float radiance (accumulation / samples, unclamped) as a little-endian PFM, bottom row first as PFM defines
+        it — which is the buffer's own row order (row 0 is the bottom of the image, main.cpp:186-187)."""
+        acc = self.getAccumulation()
+        n = np.where(acc[..., 3:4] > 0, acc[..., 3:4], np.float32(1.0))
+        rad = (acc[..., :3] / n).astype("<f4")
+        with open(path, "wb") as f:
+            f.write(f"PF\n{self.m_width} {self.m_height}\n-1.0\n".encode())
+            f.write(np.ascontiguousarray(rad).tobytes())
 
     def setAccumulation(self, acc: np.ndarray, next_frame_index: int):
         a = np.ascontiguousarray(acc, np.float32)

@@ -333,6 +333,65 @@ public:
         }
         return f.good();
     }
+    // The same image as a PNG (8-bit RGBA, filter 0, zlib "stored" blocks: no compression library needed).
+    bool savePNG(const std::string& path) const
+    {
+        std::ofstream f(path, std::ios::binary);
+        if (!f.is_open())
+            return false;
+        const auto be32 = [](uint32_t v) { return std::string{ static_cast<char>(v >> 24), static_cast<char>(v >> 16), static_cast<char>(v >> 8), static_cast<char>(v) }; };
+        const auto crc32 = [](const std::string& d) {
+            uint32_t c = 0xFFFFFFFFu;
+            for (unsigned char ch : d)
+            {
+                c ^= ch;
+                for (int k = 0; k < 8; k++)
+                    c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+            }
+            return c ^ 0xFFFFFFFFu;
+        };
+        const auto chunk = [&](const char* kind, const std::string& body) {
+            const std::string tagged = std::string(kind, 4) + body;
+            f << be32(static_cast<uint32_t>(body.size())) << tagged << be32(crc32(tagged));
+        };
+        // scanlines top to bottom (V flip), each prefixed with filter type 0; bytes r, g, b, a as packed (Renderer.h:70-78)
+        std::string raw;
+        raw.reserve((static_cast<size_t>(m_width) * 4 + 1) * m_height);
+        for (uint32_t y = 0; y < m_height; y++)
+        {
+            raw.push_back('\0');
+            const uint32_t* src = m_pixels.data() + static_cast<size_t>(m_height - 1 - y) * m_width;
+            for (uint32_t x = 0; x < m_width; x++)
+                for (int k = 0; k < 4; k++)
+                    raw.push_back(static_cast<char>((src[x] >> (8 * k)) & 0xFFu));
+        }
+        uint32_t a = 1u, b = 0u; // Adler-32 of the uncompressed stream
+        for (unsigned char ch : raw)
+        {
+            a = (a + ch) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        std::string z = "\x78\x01";
+        for (size_t off = 0; off < raw.size() || off == 0; off += 65535)
+        {
+            const size_t n = std::min<size_t>(65535, raw.size() - off);
+            const bool last = off + n >= raw.size();
+            z.push_back(last ? '\x01' : '\x00');
+            z.push_back(static_cast<char>(n & 0xFF)); z.push_back(static_cast<char>(n >> 8));
+            z.push_back(static_cast<char>(~n & 0xFF)); z.push_back(static_cast<char>((~n >> 8) & 0xFF));
+            z.append(raw, off, n);
+            if (last)
+                break;
+        }
+        z += be32((b << 16) | a);
+        f << "\x89PNG\r\n\x1a\n";
+        std::string ihdr = be32(m_width) + be32(m_height);
+        ihdr += std::string{ '\x08', '\x06', '\0', '\0', '\0' }; // 8 bits, RGBA, deflate, adaptive filtering, no interlace
+        chunk("IHDR", ihdr);
+        chunk("IDAT", z);
+        chunk("IEND", std::string());
+        return f.good();
+    }
 private:
     uint32_t m_width, m_height;
     ImageType m_type;

@@ -5,6 +5,7 @@
 //   mirror_main gpu <scene.json> W H bounces sky frames <out.bin>  -> hits(int32) acc1(f32) accK(f32) rgbaK(u32)
 //   mirror_main walk <steps.bin> <out.bin> px py pz dx dy dz fov   -> scripted Camera::onUpdate, per-step camera state
 //   mirror_main app <scene.json> <out.bin>                          -> the Ataraxia layer: frame-index behaviour of edits
+//   mirror_main image <prefix>                                      -> a test pattern through Image::savePPM / savePNG
 #include <ataraxia/Ataraxia.h>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,17 @@ int main(int argc, char** argv)
     }
     if (mode == "app" && argc >= 4)
         return appSession(argv[2], argv[3]);
+    if (mode == "image")
+    {
+        // a 37x11 test pattern (RGBA8 as the renderer packs it) through both image sinks
+        const uint32_t W = 37, H = 11;
+        std::vector<uint32_t> px(W * H);
+        for (uint32_t y = 0; y < H; y++)
+            for (uint32_t x = 0; x < W; x++)
+                px[y * W + x] = 0xFF000000u | ((x * 7u) & 0xFFu) | (((y * 23u) & 0xFFu) << 8) | ((((x + y) * 5u) & 0xFFu) << 16);
+        Image img(W, H, ImageType::RGBA, px.data());
+        return img.savePPM(std::string(argv[2]) + ".ppm") && img.savePNG(std::string(argv[2]) + ".png") ? 0 : 3;
+    }
     Scene scene = Utils::importScene(argv[2]);
     if (mode == "cpu")
     {

@@ -96,6 +96,28 @@ def test_cpp_scripted_camera_walk_matches_reference_golden(driver, tmp_path):
     assert (raw[n * 23:].view(np.uint32) == gold["walk_rays"].reshape(-1).view(np.uint32)).all()
 
 
+def test_image_sinks_cpp_and_python(driver, tmp_path):
+    """Image::savePPM / savePNG (the headless stand-in for the Vulkan texture upload, Core/src/Image.cpp:183-271):
+    both mirrors write the same pixels, top row first (the UI's V flip, main.cpp:185-187), r in the low byte
+    (Renderer.h:70-78); the PNG is read back with PIL."""
+    from PIL import Image as PILImage
+    import ataraxia_b200 as atx
+    W, H = 37, 11
+    x, y = np.meshgrid(np.arange(W, dtype=np.uint32), np.arange(H, dtype=np.uint32))
+    px = (0xFF000000 | ((x * 7) & 0xFF) | (((y * 23) & 0xFF) << 8) | ((((x + y) * 5) & 0xFF) << 16)).astype(np.uint32)
+    expect = np.stack([px & 0xFF, (px >> 8) & 0xFF, (px >> 16) & 0xFF, px >> 24], -1).astype(np.uint8)[::-1]
+    assert subprocess.run([str(driver), "image", str(tmp_path / "cpp")], capture_output=True).returncode == 0
+    img = atx.Image(W, H)
+    img.setData(px)
+    img.savePPM(str(tmp_path / "py.ppm")); img.savePNG(str(tmp_path / "py.png"))
+    for who in ("cpp", "py"):
+        png = np.asarray(PILImage.open(tmp_path / f"{who}.png"))
+        assert png.shape == (H, W, 4) and (png == expect).all(), who
+        ppm = np.asarray(PILImage.open(tmp_path / f"{who}.ppm"))
+        assert (ppm == expect[..., :3]).all(), who
+    assert (tmp_path / "cpp.ppm").read_bytes() == (tmp_path / "py.ppm").read_bytes()
+
+
 def test_cpp_missing_file_and_missing_key(driver, tmp_path):
     # a missing file is an empty Scene (Utils.cpp:178-179): no spheres, no materials
     proc = subprocess.run([str(driver), "cpu", str(tmp_path / "nope.json")], capture_output=True, text=True)

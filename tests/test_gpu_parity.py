@@ -146,11 +146,28 @@ def test_live_sample_scene(atx, W, H, bounces, sky, frames):
     _live_compare(atx, GOLDEN / "sample_scene.json", W, H, bounces, sky, frames)
 
 
+def test_config2_full_size_vs_live_reference(atx):
+    """BASELINE config 2 at its full size (1920x1080, 1024 spp, 8 bounces): the accumulation buffer after 1024
+    frames, bit for bit against 1024 Render() calls of the unmodified reference CUDA renderer (one launch of the
+    warp-queue form for frames 2..1024 on our side)."""
+    _live_compare(atx, GOLDEN / "sample_scene.json", 1920, 1080, 8, False, 1024)
+
+
 def test_live_synthetic_scenes(atx, tmp_path):
     for i, scene in enumerate([atx.synthetic.small(40, 5, seed=11), atx.synthetic.config3()]):
         p = tmp_path / f"s{i}.json"
         atx.Utils.exportScene(scene, str(p))
         _live_compare(atx, p, 320, 180, 8, i == 0, 3)
+
+
+@pytest.mark.parametrize("name,frames", [("config3", 33), ("config4", 4)])
+def test_config3_config4_full_resolution_vs_live_reference(atx, tmp_path, name, frames):
+    """BASELINE configs 3 and 4 at their full 3840x2160 (256 spheres / 16 lights; 4096 spheres), a few frames of
+    the reference (its brute-force kernel needs ~0.1-1 s per 4K frame): two-slot packed form, bit for bit."""
+    scene = getattr(atx.synthetic, name)()
+    p = tmp_path / f"{name}.json"
+    atx.Utils.exportScene(scene, str(p))
+    _live_compare(atx, p, 3840, 2160, 8, False, frames)
 
 
 def test_live_edge_scenes(atx, tmp_path):
