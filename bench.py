@@ -46,6 +46,7 @@ WORKLOADS = {
     "c1": ("sample-scene-data/scene.json 1280x720 1spp 5 bounces", 1280, 720, 1, 5),
     # config 5: the TOTAL spp is fixed and split across the ranks (strong scaling), float4 buffers NCCL-summed
     "c5": ("sample-scene-data/scene.json 7680x4320 16384spp split across the GPUs, 8 bounces", 7680, 4320, 16384, 8),
+    "cs": ("synthetic 12 spheres 3 lights 1920x1080 256spp 8 bounces (small scene, several lights)", 1920, 1080, 256, 8),
     "c16k": ("synthetic 16384 spheres (chunked TMA staging) 1920x1080 16spp 8 bounces", 1920, 1080, 16, 8),
 }
 
@@ -53,6 +54,8 @@ WORKLOADS = {
 def load_scene(atx, name):
     if name in ("c1", "c2", "c5"):
         return atx.Utils.importScene(str(ROOT / "tests" / "golden" / "sample_scene.json"))
+    if name == "cs":
+        return atx.synthetic.small(12, 3, seed=9)
     if name == "c16k":
         return atx.synthetic.stress16k()
     return atx.synthetic.config3() if name == "c3" else atx.synthetic.config4()
