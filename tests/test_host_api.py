@@ -153,6 +153,19 @@ def test_scripted_camera_walk_matches_live_reference(built, refcpu):
     assert (bits(cam.getRayDirection()) == bits(rays)).all()
 
 
+def test_camera_update_rejects_null_arguments(built):
+    import ctypes as C
+    lib = _capi.lib()
+    pos, d, last = (np.zeros(n, np.float32) for n in (3, 3, 2))
+    inp = _capi.CameraInput(0, 0, 0.0, 0.0)
+    null_f = C.POINTER(C.c_float)()
+    assert lib.atx_host_camera_update(null_f, _capi.fptr(d), _capi.fptr(last), C.byref(inp), 0.1, None) == _capi.ATX_ERR_INVALID
+    assert lib.atx_host_camera_update(_capi.fptr(pos), _capi.fptr(d), _capi.fptr(last), None, 0.1, None) == _capi.ATX_ERR_INVALID
+    assert b"null" in lib.atx_last_error()
+    assert lib.atx_host_camera_update(_capi.fptr(pos), _capi.fptr(d), _capi.fptr(last), C.byref(inp), 0.1, None) == _capi.ATX_OK
+    assert lib.atx_last_mega_kind(None, None) == _capi.ATX_ERR_INVALID
+
+
 def test_camera_update_semantics(built):
     cam = atx.Camera(45.0, 0.1, 100.0)
     p0, d0 = cam.getPosition().copy(), cam.getDirection().copy()
