@@ -28,8 +28,25 @@ def driver(built, tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="module")
+def example(built, tmp_path_factory):
+    """examples/render_scene.cpp: the headless command-line use of the C++ mirror."""
+    out = tmp_path_factory.mktemp("example") / "render_scene"
+    lib = ROOT / "ataraxia_b200" / "lib"
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "render_scene.cpp"),
+           "-o", str(out), f"-L{lib}", "-lataraxia_b200", f"-Wl,-rpath,{lib}"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return out
+
+
 def f32(x):
     return np.asarray(x, np.float64).astype(np.float32)
+
+
+def test_example_builds_and_prints_usage(example):
+    proc = subprocess.run([str(example)], capture_output=True, text=True)
+    assert proc.returncode == 2 and "usage:" in proc.stderr
 
 
 @pytest.mark.parametrize("file", ["sample_scene.json", "small_scene.json"])
@@ -182,3 +199,30 @@ def test_cpp_application_layer_matches_python(driver, tmp_path):
     acc = app.GetRenderer().getAccumulation()
     assert (np.fromfile(out, np.uint32) == acc.view(np.uint32).reshape(-1)).all()
     app.close()
+
+
+@pytest.mark.gpu
+def test_example_renders_the_same_image_as_the_python_mirror(example, tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from PIL import Image as PILImage
+    import ataraxia_b200 as atx
+    png, pfm = tmp_path / "out.png", tmp_path / "out.pfm"
+    proc = subprocess.run([str(example), str(GOLDEN / "sample_scene.json"), str(png), "--width", "200", "--height", "120", "--spp", "40",
+                           "--bounces", "6", "--sky", "1", "--pfm", str(pfm)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "Mpaths/s" in proc.stdout
+    scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    r = atx.Renderer(0)
+    r.setSettings(atx.Settings(True, True, 6))
+    r.onResize(200, 120); cam.Resize(200, 120)
+    r.Render(cam, scene, frames=40)
+    px = r.getImage().data
+    expect = np.stack([px & 0xFF, (px >> 8) & 0xFF, (px >> 16) & 0xFF, px >> 24], -1).astype(np.uint8)[::-1]
+    assert (np.asarray(PILImage.open(png)) == expect).all()
+    ref_pfm = tmp_path / "py.pfm"
+    r.saveAccumulationPFM(str(ref_pfm))
+    assert pfm.read_bytes() == ref_pfm.read_bytes()
+    r.close()
