@@ -263,16 +263,44 @@ class Scene:
     camera: Camera = field(default_factory=Camera)
 
 
+class _PinnedPixels:
+    """Owner of one atx_host_alloc block, exposed to numpy through the array interface: arrays made from it hold
+    a reference, and the block is released when the last of them is gone."""
+
+    def __init__(self, ptr: C.c_void_p, shape):
+        self._ptr = ptr
+        self.__array_interface__ = {"data": (ptr.value, False), "shape": tuple(shape), "typestr": "<u4", "version": 3}
+
+    def __del__(self):
+        try:
+            _capi.lib().atx_host_free(self._ptr)
+        except Exception:
+            pass
+
+
 class Image:
     """Headless stand-in for Core/include/Image.h: what Renderer touches (ctor, setData, getWidth/getHeight)."""
 
-    def __init__(self, width: int, height: int):
+    def __init__(self, width: int, height: int, pinned: bool = False):
         self.m_width, self.m_height = width, height
+        self._pinned = False
+        if pinned and width * height > 0:
+            # the renderer's image: page-locked, so the per-frame read-back is a single DMA
+            ptr = C.c_void_p()
+            if _capi.lib().atx_host_alloc(width * height * 4, C.byref(ptr)) == _capi.ATX_OK:
+                self.data = np.asarray(_PinnedPixels(ptr, (height, width)))   # the array (and its views) keep the block alive
+                self.data[...] = 0
+                self._pinned = True
+                return
         self.data = np.zeros((height, width), np.uint32)
 
     def getWidth(self): return self.m_width
     def getHeight(self): return self.m_height
-    def setData(self, data): self.data = data
+    def setData(self, data):
+        if self._pinned:
+            self.data[...] = np.asarray(data, np.uint32).reshape(self.m_height, self.m_width)
+        else:
+            self.data = data
 
     def savePPM(self, path: str) -> None:
         """Output sink in place of the Vulkan texture upload (Core/src/Image.cpp:183-271): binary PPM, rows top to
@@ -379,7 +407,7 @@ class Renderer:
         if self.m_image is not None and self.m_image.getWidth() == width and self.m_image.getHeight() == height:
             return
         check(_capi.lib().atx_resize(self._h, width, height))
-        self.m_image = Image(width, height)
+        self.m_image = Image(width, height, pinned=True)
         self.m_width, self.m_height = width, height
 
     def getImage(self): return self.m_image

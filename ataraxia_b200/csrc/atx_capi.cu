@@ -689,6 +689,24 @@ atx_status atx_read_rgba8(atx_handle h, uint32_t* dst, uint32_t divisor)
     return ATX_OK;
 }
 
+atx_status atx_host_alloc(size_t bytes, void** out)
+{
+    // page-locked host memory: a read-back into it is one DMA instead of a staged copy (the reference reads into
+    // pageable new[] memory, Renderer.cu:124-129, :240)
+    if (!out || bytes == 0)
+        return fail(ATX_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    ATX_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return ATX_OK;
+}
+
+atx_status atx_host_free(void* p)
+{
+    if (p)
+        ATX_CUDA(cudaFreeHost(p));
+    return ATX_OK;
+}
+
 atx_status atx_read_hit_ids(atx_handle h, int32_t* dst)
 {
     if (atx_status s = ensure_device(h))

@@ -409,8 +409,8 @@ public:
     }
     ~Renderer()
     {
+        freeImageData();
         atx_destroy(m_handle);
-        delete[] h_imageData_;
     }
     Renderer(const Renderer&) = delete; // the reference's shallow copy double-frees (DeviceMemory.h:33)
     Renderer& operator=(const Renderer&) = delete;
@@ -426,8 +426,16 @@ public:
             return;
         }
         m_image = std::make_shared<Image>(width, height, ImageType::RGBA);
-        delete[] h_imageData_;
-        h_imageData_ = new uint32_t[static_cast<size_t>(width) * height];
+        freeImageData();
+        // page-locked where possible (the per-frame read-back is then one DMA); the reference uses new[] (Renderer.cu:124-129)
+        void* pinned = nullptr;
+        if (atx_host_alloc(static_cast<size_t>(width) * height * sizeof(uint32_t), &pinned) == ATX_OK)
+        {
+            h_imageData_ = static_cast<uint32_t*>(pinned);
+            m_imagePinned = true;
+        }
+        else
+            h_imageData_ = new uint32_t[static_cast<size_t>(width) * height];
         m_width = width;
         m_height = height;
     }
@@ -529,10 +537,20 @@ public:
 
 private:
     static void report(const char* where) { std::cerr << "ataraxia_b200 (" << where << "): " << atx_last_error() << std::endl; }
+    void freeImageData()
+    {
+        if (m_imagePinned)
+            atx_host_free(h_imageData_);
+        else
+            delete[] h_imageData_;
+        h_imageData_ = nullptr;
+        m_imagePinned = false;
+    }
 
     atx_handle m_handle = nullptr;
     std::shared_ptr<Image> m_image;
     uint32_t* h_imageData_ = nullptr;
+    bool m_imagePinned = false;
     uint32_t m_width = 0, m_height = 0;
     Settings m_settings;
     const Scene* m_scene = nullptr;

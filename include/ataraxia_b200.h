@@ -236,6 +236,11 @@ ATX_API atx_status atx_reset_counters(atx_handle h);
 ATX_API atx_status atx_accum_device_ptr(atx_handle h, void** out);
 ATX_API atx_status atx_stream(atx_handle h, void** out_cuda_stream);
 
+/* Page-locked host memory for read-back destinations (atx_read_rgba8, atx_read_accum): the copy becomes one DMA
+ * instead of a staged one. Optional: every read function takes any host pointer. Needs a CUDA device. */
+ATX_API atx_status atx_host_alloc(size_t bytes, void** out);
+ATX_API atx_status atx_host_free(void* p);
+
 /* ---- multi-GPU: spp split + sum of accumulation buffers over NVLink ------- */
 
 /* 128-byte NCCL unique id (rank 0 creates, the host broadcasts it). */
