@@ -934,8 +934,10 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in. The path
                     // state of this branch IS the per-pixel constants plus a seed and a direction, so it is kept in
                     // its own registers and queued from them (no copy into a PathState)
-#if ATX_WQ_GUNROLL
+#if ATX_WQ_GUNROLL == 1
 #pragma unroll
+#elif ATX_WQ_GUNROLL == 2
+#pragma unroll 2
 #else
 #pragma unroll 1
 #endif

@@ -42,3 +42,28 @@ def refcpu(built):
 @pytest.fixture(scope="session")
 def sample_scene_path():
     return GOLDEN / "sample_scene.json"
+
+
+def random_graph_scene(atx, rng):
+    """A random three-level scene graph: arbitrary (unnormalised) quaternions, non-uniform and negative scales,
+    nested translations, several spheres per node (some with out-of-range material ids)."""
+    import numpy as np
+    scene = atx.Scene()
+    scene.materials = [atx.Material(albedo=tuple(rng.uniform(0, 1, 3)), roughness=float(rng.uniform(0, 1))) for _ in range(3)]
+    scene.lights = [atx.Light((1.0, 5.0, 2.0), (1.0, 1.0, 1.0), 1.0)]
+    scene.camera = atx.Camera(45.0, 0.1, 100.0, (0.0, 1.0, 8.0), (0.0, 0.0, -1.0))
+
+    def fill(node, depth):
+        node.setPosition(rng.normal(0, 3, 3))
+        node.setRotation(rng.normal(0, 1, 4) if rng.random() < 0.8 else np.zeros(4))   # all-zero = identity quirk
+        node.setScale(rng.uniform(0.2, 3.0, 3) * rng.choice([1.0, 1.0, -1.0], 3))
+        for _ in range(int(rng.integers(0, 4))):
+            node.addSphere(atx.Sphere(tuple(rng.normal(0, 2, 3)), float(rng.uniform(0.1, 2.0)), int(rng.integers(-1, 5))))
+        if depth < 3:
+            for k in range(int(rng.integers(1, 3))):
+                child = atx.SceneNode(f"n{depth}_{k}")
+                fill(child, depth + 1)
+                node.addChild(child)
+
+    fill(scene.rootNode, 0)
+    return scene

@@ -83,6 +83,24 @@ def test_cpp_host_side_matches_python_mirror(driver, built, tmp_path, file):
     assert json.loads(exported.read_text()) == atx.Utils.serializeScene(scene)
 
 
+def test_cpp_flattens_random_scene_graphs_like_python(driver, built, tmp_path):
+    """Nested nodes with arbitrary quaternions and negative scales through the C++ mirror's importer and traversal."""
+    import ataraxia_b200 as atx
+    from conftest import random_graph_scene
+    rng = np.random.default_rng(4242)
+    for trial in range(3):
+        p = tmp_path / f"graph{trial}.json"
+        atx.Utils.exportScene(random_graph_scene(atx, rng), str(p))
+        proc = subprocess.run([str(driver), "cpu", str(p)], capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stderr
+        g = np.array(json.loads(proc.stdout)["spheres"], np.float64)
+        spheres = atx.pack_spheres(atx.traverseSceneGraph(atx.Utils.importScene(str(p)).rootNode))
+        assert len(g) == len(spheres) and len(g) > 0
+        assert (f32(g[:, :3]).view(np.uint32) == spheres["center"].view(np.uint32)).all()
+        assert (f32(g[:, 3]).view(np.uint32) == spheres["radius"].view(np.uint32)).all()
+        assert (g[:, 4].astype(np.int32) == spheres["material"]).all()
+
+
 def test_reference_reads_the_cpp_export(driver, refcpu, tmp_path):
     """The reference's own Utils::importScene + traverseSceneGraph on a file written by the C++ mirror."""
     import ataraxia_b200 as atx
