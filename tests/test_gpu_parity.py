@@ -285,7 +285,9 @@ def test_warp_queue_form_is_bit_identical(atx):
              (atx.synthetic.small(8, 1, seed=6), 64, 40, 8, False, 17),
              (atx.synthetic.small(12, 3, seed=9), 97, 55, 8, True, 48),
              (atx.synthetic.small(16, 0, seed=7), 80, 48, 5, True, 40),
-             (atx.synthetic.small(5, 2, seed=3), 33, 9, 6, False, 1)]
+             (atx.synthetic.small(5, 2, seed=3), 33, 9, 6, False, 1),
+             (atx.synthetic.small(40, 1, seed=21), 96, 54, 6, True, 36),      # more spheres than the automatic choice allows
+             (atx.synthetic.small(8, 1, seed=6), 64, 40, 0, False, 40)]      # maxBounces 0: every sample black
     for scene, W, H, bounces, sky, frames in cases:
         r, cam = setup(atx, scene, W, H, bounces, sky)
         r.uploadScene(scene); r.setCamera(cam)
