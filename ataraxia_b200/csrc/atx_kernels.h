@@ -22,7 +22,9 @@ constexpr int kMegaWhileWhile = 1; // one pixel per thread, hits gathered before
 constexpr int kMegaPair = 2;       // two pixels per thread, packed f32x2 sphere loop
 constexpr int kMegaWarpQueue = 3;  // one tile per warp, hits queued in shared memory and bounced 32 at a time
 constexpr uint32_t kWhileWhileMaxSpheres = 16;
-constexpr uint32_t kWarpQueueMinFrames = 32; // frames per launch from which the warp-queue form replaces the while-while form
+constexpr uint32_t kWarpQueueMinFrames = 4;  // frames per launch from which the warp-queue form replaces the while-while form
+                                             // (config 2 geometry, ms per launch, while-while / warp-queue: 1 frame 0.128 / 0.156,
+                                             // 2: 0.169 / 0.179, 4: 0.257 / 0.237, 8: 0.428 / 0.324, 32: 1.36 / 1.10, 1024: 31.1 / 22.6)
 
 cudaError_t configure();
 int mega_kind(const atxk::RenderParams& p, int requested);

@@ -147,7 +147,7 @@ enum {
                                    packed (two pixels per thread, f32x2 sphere loop), 3 = warp-queue
                                    (one 8x4 tile per warp, hits queued in shared memory and bounced 32
                                    at a time; the automatic choice for <= 16 spheres, at most one light
-                                   and >= 32 frames per launch) */
+                                   and >= 4 frames per launch) */
     ATX_TUNE_PARK_THRESHOLD = 3 /* while-while form: parked hits per warp (1..32) that trigger the
                                    bounce phase (default 8) */,
     ATX_TUNE_CLAIM_THRESHOLD = 4 /* idle lanes per warp (1..32) that trigger a batched claim from the
