@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -90,6 +90,11 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi is already running (it takes ~0.1 s to produce its first
+        row), only rows from here on count."""
+        self.rows = []
 
     def stop(self):
         if self.proc:
@@ -309,13 +314,14 @@ def main():
     calibration = None
     if args.variant == "auto":
         calibration = r.calibrate(2)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     r.sync()
     r.resetCounters()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     wall0 = time.perf_counter()
     dev_ms = []
     for _ in range(args.steps):
