@@ -39,6 +39,22 @@ def test_library_exports_every_declared_symbol(built):
     assert b"sm_100a" in lib.atx_version()
 
 
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/ataraxia_b200.h as a C11 translation unit (-pedantic -Werror), linked against the library and run
+    (host helpers only: no GPU needed) — the view a cgo / JNI / ctypes binding has of the boundary."""
+    import subprocess
+    lib = ROOT / "ataraxia_b200" / "lib"
+    exe = tmp_path / "c_abi"
+    proc = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c" / "c_abi.c"),
+                           "-o", str(exe), f"-L{lib}", "-lataraxia_b200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    # W + D for 0.1 s at speed 5 from (0,0,3) looking down -z, then the mouse look: forward 0.5, right 0.5
+    x, y, z = (float(v) for v in run.stdout.split()[-3:])
+    assert abs(x - 0.5) < 1e-6 and y == 0.0 and abs(z - 2.5) < 1e-6
+
+
 def test_no_cpu_fallback(built):
     """Without a CUDA device the product refuses to create a renderer (and says why)."""
     import torch
