@@ -23,7 +23,7 @@ SYMBOLS = [
     "atx_render", "atx_render_frames", "atx_calibrate", "atx_sync", "atx_last_render_ms", "atx_last_mega_kind", "atx_event_record", "atx_event_elapsed_ms",
     "atx_read_accum", "atx_write_accum", "atx_read_rgba8", "atx_read_hit_ids", "atx_read_ray_directions",
     "atx_get_counters", "atx_reset_counters", "atx_accum_device_ptr", "atx_stream", "atx_host_alloc", "atx_host_free",
-    "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum",
+    "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum", "atx_allreduce_preview", "atx_read_preview",
     "atx_host_camera_matrices", "atx_host_ray_directions", "atx_host_node_transform", "atx_host_transform_sphere", "atx_host_mat4_mul",
     "atx_host_camera_update",
 ]
@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
         "atx_comm_init_rank": [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)],
         "atx_comm_destroy": [vp],
         "atx_allreduce_accum": [vp],
+        "atx_allreduce_preview": [vp],
+        "atx_read_preview": [vp, vp, vp, C.c_uint32],
         "atx_last_mega_kind": [vp, C.POINTER(C.c_int)],
         "atx_host_alloc": [C.c_size_t, C.POINTER(vp)],
         "atx_host_free": [vp],

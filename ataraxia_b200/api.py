@@ -547,6 +547,17 @@ class Renderer:
         check(_capi.lib().atx_comm_init_rank(self._h, n_ranks, rank, buf))
 
     def commDestroy(self): check(_capi.lib().atx_comm_destroy(self._h))
+
+    def allreducePreview(self):
+        """Sum of all ranks' accumulation buffers into the preview buffer; the ranks' own sums stay as they are."""
+        check(_capi.lib().atx_allreduce_preview(self._h))
+
+    def getPreview(self, divisor: int):
+        """(float4 sums, RGBA8 image resolved with `divisor` = total samples per pixel) of the last preview."""
+        acc = np.empty((self.m_height, self.m_width, 4), np.float32)
+        rgba = np.empty((self.m_height, self.m_width), np.uint32)
+        check(_capi.lib().atx_read_preview(self._h, vptr(acc), vptr(rgba), int(divisor)))
+        return acc, rgba
     def allreduceAccum(self): check(_capi.lib().atx_allreduce_accum(self._h))
 
 

@@ -118,6 +118,7 @@ struct atx_renderer
     uint32_t width = 0, height = 0;
     float4* dAccum = nullptr;
     uint32_t* dRgba = nullptr;
+    float4* dPreview = nullptr; // progressive multi-GPU preview: sum over ranks of the accumulation buffers, out of place
     int32_t* dHit = nullptr;   // lazily allocated debug buffers
     float* dRays = nullptr;
     unsigned long long* dCounters = nullptr;
@@ -270,7 +271,7 @@ atx_status atx_destroy(atx_handle h)
     cudaStreamSynchronize(h->stream);
     if (h->comm && nccl().ok)
         nccl().CommDestroy(h->comm);
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
@@ -291,8 +292,8 @@ atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height)
     if (h->dAccum && h->width == width && h->height == height)
         return ATX_OK; // Renderer.cu:100-101
     ATX_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dHit); cudaFree(h->dRays);
-    h->dAccum = nullptr; h->dRgba = nullptr; h->dHit = nullptr; h->dRays = nullptr;
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays);
+    h->dAccum = nullptr; h->dRgba = nullptr; h->dPreview = nullptr; h->dHit = nullptr; h->dRays = nullptr;
     const size_t P = static_cast<size_t>(width) * height;
     ATX_CUDA(cudaMalloc(&h->dAccum, P * sizeof(float4)));
     ATX_CUDA(cudaMalloc(&h->dRgba, P * sizeof(uint32_t)));
@@ -855,6 +856,51 @@ atx_status atx_allreduce_accum(atx_handle h)
     ncclResult_t r = nccl().AllReduce(h->dAccum, h->dAccum, count, ncclFloat32, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess)
         return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+    return ATX_OK;
+}
+
+// Progressive preview across ranks: the sum of every rank's accumulation buffer WITHOUT touching
+// the buffers themselves, so each rank keeps adding its own frames afterwards. One out-of-place ncclAllReduce
+// into a second float4 buffer (a plain device copy when the handle has no communicator).
+atx_status atx_allreduce_preview(atx_handle h)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "no image");
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    if (!h->dPreview)
+        ATX_CUDA(cudaMalloc(&h->dPreview, P * sizeof(float4)));
+    if (!h->comm)
+    {
+        ATX_CUDA(cudaMemcpyAsync(h->dPreview, h->dAccum, P * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+        return ATX_OK;
+    }
+    ncclResult_t r = nccl().AllReduce(h->dAccum, h->dPreview, P * 4, ncclFloat32, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+    return ATX_OK;
+}
+
+atx_status atx_read_preview(atx_handle h, float* accum_dst, uint32_t* rgba_dst, uint32_t divisor)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!h->dPreview)
+        return fail(ATX_ERR_INVALID, "no preview: call atx_allreduce_preview");
+    if (rgba_dst && divisor == 0)
+        return fail(ATX_ERR_INVALID, "the preview needs the total sample count as divisor");
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    if (accum_dst)
+        ATX_CUDA(cudaMemcpyAsync(accum_dst, h->dPreview, P * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (rgba_dst)
+    {
+        // the display buffer is scratch between renders: the next render or atx_read_rgba8 rewrites it
+        ATX_CUDA(atx_launch::resolve_rgba(h->dPreview, h->dRgba, static_cast<uint32_t>(P), divisor, h->stream));
+        h->launches++;
+        ATX_CUDA(cudaMemcpyAsync(rgba_dst, h->dRgba, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
     return ATX_OK;
 }
 

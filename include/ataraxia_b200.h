@@ -252,6 +252,15 @@ ATX_API atx_status atx_comm_destroy(atx_handle h);
  * handle's stream (count = 4*width*height). .w sums to the exact total spp. */
 ATX_API atx_status atx_allreduce_accum(atx_handle h);
 
+/* Progressive preview across ranks: the sum of every rank's accumulation buffer into a separate preview buffer
+ * (one out-of-place ncclAllReduce on the handle's stream; a device copy without a communicator). The ranks' own
+ * buffers are not touched, so rendering continues afterwards — what a live multi-GPU view of a long render
+ * needs (the reference shows its single buffer every frame, Renderer.cu:165-168, main.cpp:185-187). */
+ATX_API atx_status atx_allreduce_preview(atx_handle h);
+/* Read the preview: the float4 sums (accum_dst, may be NULL) and/or the RGBA8 image resolved with
+ * `divisor` = total samples per pixel over all ranks (rgba_dst, may be NULL). Overwrites the display buffer. */
+ATX_API atx_status atx_read_preview(atx_handle h, float* accum_dst, uint32_t* rgba_dst, uint32_t divisor);
+
 /* ---- host math helpers ------------------------------------------------------
  * CPU-side pieces of the reference's HOST API (they run on the CPU in the reference
  * too), compiled inside this library so the caller's compiler flags cannot perturb

@@ -29,10 +29,27 @@ def main():
     uid = [atx.Renderer.commUniqueId() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     r.commInitRank(world, rank, uid[0])
+    # progressive preview: every rank renders the first half of its share, the out-of-place sum is looked at, the
+    # ranks' own buffers are untouched, and rendering goes on to the full share
+    from ataraxia_b200.distributed import frame_partition
+    sh = frame_partition(total, rank, world)
+    half = sh.count // 2
+    r.renderFrames(sh.first, half, sh.stride, zero_first=True)
+    own_before = r.getAccumulation()
+    r.allreducePreview()
+    done = torch.tensor([half], device=f"cuda:{local}"); dist.all_reduce(done)
+    prev_acc, prev_rgba = r.getPreview(int(done.item()))
+    preview_ok = bool((prev_acc[..., 3] == int(done.item())).all()) and bool((r.getAccumulation().view(np.uint32) == own_before.view(np.uint32)).all())
+    preview_ok &= bool(((prev_rgba >> 24) == 255).all())
+    r.renderFrames(sh.first + half * sh.stride, sh.count - half, sh.stride, zero_first=False)
+    continued = r.getAccumulation()
     share = render_split(r, total, rank, world)          # frames rank+1, rank+1+world, ... then NCCL sum
     reduced = r.getAccumulation()
     rgba = r.getRGBA8(divisor=total)
-    ok = True
+    ok = preview_ok
+    # the share rendered in two launches around the preview equals the share rendered in one (render_split re-renders it)
+    r.renderFrames(sh.first, sh.count, sh.stride, zero_first=True)
+    ok &= bool((r.getAccumulation().view(np.uint32) == continued.view(np.uint32)).all())
     if rank == 0:
         r.renderFrames(1, total, 1, zero_first=True)
         seq = r.getAccumulation()
@@ -41,7 +58,7 @@ def main():
         ok &= bool(np.allclose(reduced[..., :3], seq[..., :3], rtol=2e-6, atol=1e-6))   # float reassociation only
         d = np.abs(((rgba >> 8) & 0xFF).astype(int) - ((rgba_seq >> 8) & 0xFF).astype(int))
         ok &= bool(d.max() <= 1)
-        print(f"MGPU world={world} total={total} share0={share.count} counts_ok={(reduced[..., 3] == total).all()} "
+        print(f"MGPU world={world} total={total} share0={share.count} preview_ok={preview_ok} counts_ok={(reduced[..., 3] == total).all()} "
               f"max_abs_diff={np.abs(reduced[..., :3] - seq[..., :3]).max():.3e} rgba_lsb={d.max()} ok={ok}", flush=True)
     # every rank holds the same reduced buffer
     t = torch.from_numpy(reduced.copy()).cuda()

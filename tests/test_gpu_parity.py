@@ -518,6 +518,29 @@ def test_application_default_scene_vs_live_reference(atx, tmp_path):
     app.close()
 
 
+def test_progressive_preview_leaves_the_accumulation_alone(atx):
+    """atx_allreduce_preview on a handle without a communicator (one rank): the preview is a copy of the sums, it can
+    be resolved with its own divisor, and the render continues from the untouched accumulation buffer."""
+    scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
+    r, cam = setup(atx, scene, 160, 90, 6, True)
+    with pytest.raises(atx.AtxError):
+        r.getPreview(1)                                              # no preview yet
+    r.Render(cam, scene, frames=5)
+    before = r.getAccumulation()
+    r.allreducePreview()
+    acc, rgba = r.getPreview(5)
+    assert (bits(acc) == bits(before)).all() and (rgba == r.getRGBA8(divisor=5)).all()
+    assert (bits(r.getAccumulation()) == bits(before)).all()
+    r.Render(cam, scene, frames=3)                                   # frames 6..8 on top of the same sums
+    r2, cam2 = setup(atx, scene, 160, 90, 6, True)
+    r2.Render(cam2, scene, frames=8)
+    assert (bits(r.getAccumulation()) == bits(r2.getAccumulation())).all()
+    assert (bits(r.getPreview(5)[0]) == bits(before)).all()          # the preview is a snapshot
+    with pytest.raises(atx.AtxError):
+        r.getPreview(0)                                              # the RGBA8 preview needs the total sample count
+    r.close(); r2.close()
+
+
 def test_error_behaviour(atx):
     r = atx.Renderer(0)
     with pytest.raises(atx.AtxError):
