@@ -135,6 +135,20 @@ class OraclePort(_CpuOracle):
         fr(_f(ip), _f(iv), W, H, _p(rays), threads)
         return rays, ip, iv
 
+    def camera_walk(self, pos, direction, steps):
+        """Camera::onUpdate (Camera.cpp:30-108) over a scripted input sequence (CAMERA_STEP_DTYPE): per-step
+        positions, directions and moved flags."""
+        steps = np.ascontiguousarray(steps, CAMERA_STEP_DTYPE)
+        p, d, last = _f32(pos, 3).copy(), _f32(direction, 3).copy(), np.zeros(2, np.float32)
+        fn = self.lib.orc_camera_update
+        fn.restype = C.c_int
+        fn.argtypes = [_fp, _fp, _fp, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_float]
+        op, od, om = np.empty((len(steps), 3), np.float32), np.empty((len(steps), 3), np.float32), np.empty(len(steps), bool)
+        for i, st in enumerate(steps):
+            om[i] = bool(fn(_f(p), _f(d), _f(last), int(st["keys"]), int(st["right"]), float(st["mouse_x"]), float(st["mouse_y"]), float(st["dt"])))
+            op[i], od[i] = p, d
+        return op, od, om
+
     def node_transform(self, parent, position, rot_xyzw, scale):
         out = np.empty(16, np.float32)
         fn = self.lib.orc_node_transform

@@ -8,6 +8,7 @@
 // What it restates, function by function (reference file:line in each comment):
 //   Random::PcgHash / PcgFloat          Core/include/Random.h:59-70
 //   Camera matrices + ray table         Engine/src/Camera.cpp:134-195 (glm 1.0.2 order)
+//   Camera::onUpdate (scripted input)   Engine/src/Camera.cpp:30-108
 //   SceneNode transform / flatten       Engine/src/SceneNode.cpp:42-59, Renderer.cu:67-96
 //   Renderer::traceRay / rayHit         Engine/src/Renderer.cu:251-285, :396-409
 //   Renderer::perPixel                  Engine/src/Renderer.cu:287-387
@@ -379,6 +380,62 @@ extern "C" {
 
 uint32_t orc_pcg_hash(uint32_t seed) { return pcg_hash(seed); }
 float orc_pcg_float(uint32_t* seed) { return pcg_float(*seed); }
+
+// Camera::onUpdate, Camera.cpp:30-108, with the window queries replaced by arguments: keys W=1 S=2 A=4 D=8 Q=16 E=32,
+// right = MouseButton::Right held, (mouseX, mouseY) = Input::GetMousePosition(). glm pieces in their own order:
+// angleAxis (ext/quaternion_trigonometric.inl:30-36), cross(quat, quat) and normalize(quat)
+// (ext/quaternion_geometric.inl:11-34, dot as (w*w + x*x) + (y*y + z*z), detail/type_quat.inl:17-24), quat * vec3
+// (detail/type_quat.inl:359-366). Returns what onUpdate returns.
+int orc_camera_update(float pos[3], float dir[3], float lastMouse[2], uint32_t keys, int right, float mouseX, float mouseY, float dt)
+{
+    const float dx = (mouseX - lastMouse[0]) * 0.002f, dy = (mouseY - lastMouse[1]) * 0.002f; // :33-35
+    lastMouse[0] = mouseX;
+    lastMouse[1] = mouseY;
+    if (!right)
+        return 0; // :37-41
+    bool moved = false;
+    v3 p{ pos[0], pos[1], pos[2] }, d{ dir[0], dir[1], dir[2] };
+    const v3 up{ 0.0f, 1.0f, 0.0f };
+    const v3 rightV = cross(d, up); // :47
+    const float speed = 5.0f;
+    if (keys & 1u) { p = p + d * speed * dt; moved = true; }        // W :51-56
+    else if (keys & 2u) { p = p - d * speed * dt; moved = true; }   // S
+    if (keys & 4u) { p = p - rightV * speed * dt; moved = true; }   // A :64-69
+    else if (keys & 8u) { p = p + rightV * speed * dt; moved = true; }
+    if (keys & 16u) { p = p - up * speed * dt; moved = true; }      // Q :77-82
+    else if (keys & 32u) { p = p + up * speed * dt; moved = true; }
+    if (dx != 0.0f || dy != 0.0f) // :90-100
+    {
+        const float yaw = dx * 0.3f, pitch = dy * 0.3f;
+        struct Q { float w, x, y, z; };
+        const auto angleAxis = [](float angle, v3 axis) {
+            const float sn = std::sin(angle * 0.5f);
+            const v3 vs = axis * sn;
+            return Q{ std::cos(angle * 0.5f), vs.x, vs.y, vs.z };
+        };
+        const Q q1 = angleAxis(-pitch, rightV), q2 = angleAxis(-yaw, v3{ 0.0f, 1.0f, 0.0f });
+        Q c{ q1.w * q2.w - q1.x * q2.x - q1.y * q2.y - q1.z * q2.z,
+             q1.w * q2.x + q1.x * q2.w + q1.y * q2.z - q1.z * q2.y,
+             q1.w * q2.y + q1.y * q2.w + q1.z * q2.x - q1.x * q2.z,
+             q1.w * q2.z + q1.z * q2.w + q1.x * q2.y - q1.y * q2.x };
+        const float len = std::sqrt((c.w * c.w + c.x * c.x) + (c.y * c.y + c.z * c.z));
+        if (len <= 0.0f)
+            c = Q{ 1.0f, 0.0f, 0.0f, 0.0f };
+        else
+        {
+            const float inv = 1.0f / len;
+            c = Q{ c.w * inv, c.x * inv, c.y * inv, c.z * inv };
+        }
+        const v3 qv{ c.x, c.y, c.z };
+        const v3 uv = cross(qv, d);
+        const v3 uuv = cross(qv, uv);
+        d = d + ((uv * c.w) + uuv) * 2.0f;
+        moved = true;
+    }
+    pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+    dir[0] = d.x; dir[1] = d.y; dir[2] = d.z;
+    return moved ? 1 : 0;
+}
 
 // Camera.cpp:134-159 (perspectiveRH_NO: glm/ext/matrix_clip_space.inl:249-262; lookAtRH: ext/matrix_transform.inl:153-173)
 void orc_camera_matrices(const float pos[3], const float dir[3], float fov, float nearClip, float farClip,

@@ -160,3 +160,30 @@ def test_port_equals_reference_live(port, refcpu, tmp_path):
         assert (refcpu.pack_rgba8(a, 3) == port.pack_rgba8(b, 3)).all()
     for seed in (0, 1, 77, 0xDEADBEEF):
         assert refcpu.pcg_hash(seed) == port.pcg_hash(seed)
+
+
+def test_camera_update_port_matches_reference_golden_and_product(port, gold):
+    """The port's Camera::onUpdate (Camera.cpp:30-108) against the reference's per-step camera states (golden, 160
+    scripted steps) and, on a second random script, against the product's host helper (atx_host_camera_update)."""
+    from oracle.bindings import CAMERA_STEP_DTYPE
+    import ataraxia_b200 as atx
+    steps = gold["walk_steps"].view(CAMERA_STEP_DTYPE)
+    op, od, om = port.camera_walk(gold["sample_campos"], gold["sample_camdir"], steps)
+    assert (op.view(np.uint32) == gold["walk_pos"].view(np.uint32)).all()
+    assert (od.view(np.uint32) == gold["walk_dir"].view(np.uint32)).all()
+    assert (om == gold["walk_moved"]).all()
+    rng = np.random.default_rng(99)
+    n = 400
+    steps = np.zeros(n, CAMERA_STEP_DTYPE)
+    steps["dt"] = rng.uniform(0.0, 0.2, n)
+    steps["mouse_x"] = np.cumsum(rng.normal(0, 60, n)); steps["mouse_y"] = np.cumsum(rng.normal(0, 60, n))
+    steps["keys"] = rng.integers(0, 64, n); steps["right"] = rng.random(n) < 0.75
+    start_p, start_d = np.array([1.0, 2.0, 3.0], np.float32), np.array([0.3, -0.2, -0.93], np.float32)
+    op, od, om = port.camera_walk(start_p, start_d, steps)
+    cam = atx.Camera(50.0, 0.1, 100.0, start_p, start_d)
+    for i, st in enumerate(steps):
+        keys = "".join(c for b, c in enumerate("WSADQE") if (int(st["keys"]) >> b) & 1)
+        moved = cam.onUpdate(float(st["dt"]), atx.InputState(keys, (float(st["mouse_x"]), float(st["mouse_y"])), bool(st["right"])))
+        assert moved == om[i]
+        assert (cam.getPosition().view(np.uint32) == op[i].view(np.uint32)).all(), i
+        assert (cam.getDirection().view(np.uint32) == od[i].view(np.uint32)).all(), i
