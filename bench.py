@@ -390,6 +390,13 @@ def main():
                 traffic = json.loads(tpath.read_text()).get(args.workload)
             except Exception:
                 traffic = None
+        ncu_issue = None
+        ipath = ROOT / "profiles" / "issue.json"
+        if ipath.exists():
+            try:
+                ncu_issue = json.loads(ipath.read_text()).get(args.workload)
+            except Exception:
+                ncu_issue = None
         line = {
             "metric": "Mpaths/s", "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -408,7 +415,7 @@ def main():
                     "h2d_bytes_per_step": int(spheres.nbytes + mats.nbytes + lights.nbytes + 2 * 64 + 12),
                     "d2h_bytes_per_step": int(W * H * 4), "steps": e2e_steps},
             "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP32_PEAK_TFLOPS, "traffic": traffic,
+                         "frac": achieved / FP32_PEAK_TFLOPS, "traffic": traffic, "ncu": ncu_issue,
                          "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm 1965 MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                         "no tensor-core or HBM bound applies to this kernel",
                          "algorithmic": "19 flop per executed ray-sphere test + 7 per traced ray, exact device counters",
