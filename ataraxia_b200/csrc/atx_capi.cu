@@ -18,6 +18,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -56,15 +58,11 @@ struct NcclApi
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
+    std::string loadError;
 };
 
-NcclApi& nccl()
+void load_nccl(NcclApi& api)
 {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried)
-        return api;
-    tried = true;
     // a process that already carries NCCL (e.g. torch's bundled copy) gets that same
     // instance back from dlopen by soname; otherwise the system library is loaded
     const char* names[] = { "libnccl.so.2", "libnccl.so" };
@@ -75,13 +73,26 @@ NcclApi& nccl()
             break;
     }
     if (!api.lib)
-        return api;
+    {
+        const char* why = dlerror();
+        api.loadError = why ? why : "libnccl.so.2 not found";
+        return;
+    }
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    if (!api.ok)
+        api.loadError = "symbols missing";
+}
+
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static std::once_flag once; // handles on several devices may be driven from several threads
+    std::call_once(once, load_nccl, std::ref(api));
     return api;
 }
 
@@ -146,6 +157,7 @@ struct atx_renderer
     uint32_t parkThreshold = 8;  // tuning: parked hits per warp that trigger the bounce phase (while-while form)
     uint32_t claimThreshold = 0; // tuning: idle lanes per warp that trigger a batched pixel claim (0 = per form)
     uint64_t launches = 0;
+    bool calibrating = false;   // atx_calibrate's scratch launches: no counters
 
     ncclComm_t comm = nullptr;
     int nRanks = 1, rank = 0;
@@ -157,6 +169,8 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
 {
     if (h->width == 0 || h->height == 0)
         return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    if (!h->dAccum || !h->dRgba)
+        return fail(ATX_ERR_INVALID, "no image buffers (a failed atx_resize leaves the handle without an image)");
     if (!h->cam.set)
         return fail(ATX_ERR_INVALID, "no camera: call atx_set_camera or atx_set_camera_matrices");
     std::memset(&p, 0, sizeof(p));
@@ -173,7 +187,7 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
     p.lights = h->dLights;
     p.accum = h->dAccum;
     p.rgba = h->dRgba;
-    p.counters = h->dCounters;
+    p.counters = h->calibrating ? nullptr : h->dCounters; // calibration launches are not the caller's paths
     // shared-memory plan: whole scene if it fits the two-CTAs-per-SM budget, else chunks
     uint32_t chunk = h->nS;
     const uint32_t fit = atx_launch::kSmemBudgetTwoCtas / sizeof(float4);
@@ -292,11 +306,27 @@ atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height)
     if (h->dAccum && h->width == width && h->height == height)
         return ATX_OK; // Renderer.cu:100-101
     ATX_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays);
-    h->dAccum = nullptr; h->dRgba = nullptr; h->dPreview = nullptr; h->dHit = nullptr; h->dRays = nullptr;
+    // the size-dependent scratch goes first (it is re-created on demand), then the new image is allocated BEFORE the
+    // old one is given up: a failed allocation leaves the handle exactly as it was (old size, old buffers)
+    cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dWave);
+    h->dPreview = nullptr; h->dHit = nullptr; h->dRays = nullptr; h->dWave = nullptr;
+    h->waveBytes = 0;
     const size_t P = static_cast<size_t>(width) * height;
-    ATX_CUDA(cudaMalloc(&h->dAccum, P * sizeof(float4)));
-    ATX_CUDA(cudaMalloc(&h->dRgba, P * sizeof(uint32_t)));
+    float4* newAccum = nullptr;
+    uint32_t* newRgba = nullptr;
+    cudaError_t e = cudaMalloc(&newAccum, P * sizeof(float4));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&newRgba, P * sizeof(uint32_t));
+    if (e != cudaSuccess)
+    {
+        cudaFree(newAccum);
+        cudaGetLastError(); // the failed allocation is reported here, not by the next launch
+        return fail(ATX_ERR_ALLOC, "atx_resize(%u, %u): %s; the %ux%u image is kept", width, height, cudaGetErrorString(e),
+                    h->width, h->height);
+    }
+    cudaFree(h->dAccum); cudaFree(h->dRgba);
+    h->dAccum = newAccum;
+    h->dRgba = newRgba;
     ATX_CUDA(cudaMemsetAsync(h->dAccum, 0, P * sizeof(float4), h->stream));
     ATX_CUDA(cudaMemsetAsync(h->dRgba, 0, P * sizeof(uint32_t), h->stream));
     h->width = width;
@@ -321,6 +351,10 @@ atx_status atx_upload_scene(atx_handle h, const atx_sphere* spheres, size_t n_sp
         return fail(ATX_ERR_INVALID, "null array with non-zero count");
     if (n_spheres > 0x7fffffffu || n_materials > 0x7fffffffu || n_lights > 0x7fffffffu)
         return fail(ATX_ERR_INVALID, "scene too large");
+    if (n_spheres && !n_materials)
+        // the reference clamps every id to 0 and then reads materials[0] of an empty array (Renderer.cu:30-37, :326):
+        // undefined there, refused here
+        return fail(ATX_ERR_INVALID, "%zu spheres but no materials: every sphere needs a material to shade with", n_spheres);
     static_assert(sizeof(atx_sphere) == 20 && sizeof(atx_material) == 52 && sizeof(atx_light) == 28, "POD layout");
     size_t c;
     c = h->capS; if (atx_status s = grow(h->dSphAoS, c, n_spheres, 5)) return s;
@@ -497,6 +531,7 @@ atx_status atx_render(atx_handle h, uint32_t n_frames, int variant)
         return s;
     if (n_frames == 0)
         return ATX_OK;
+    h->timed = false; // until this call has recorded both events
     ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
     if (h->accumulation)
     {
@@ -528,6 +563,9 @@ atx_status atx_render_frames(atx_handle h, uint32_t first_frame, uint32_t n_fram
         return s;
     if (frame_stride == 0)
         return fail(ATX_ERR_INVALID, "frame_stride must be >= 1");
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    h->timed = false;
     ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
     if (n_frames == 0)
     {
@@ -559,6 +597,10 @@ atx_status atx_calibrate(atx_handle h, uint32_t n_frames, float* megakernel_ms, 
     const size_t bytes = static_cast<size_t>(h->width) * h->height * sizeof(float4);
     ATX_CUDA(cudaMalloc(&scratch, bytes));
     h->dAccum = scratch;
+    // the caller's counters, launch count and "last form" describe the caller's renders, not these
+    h->calibrating = true;
+    const uint64_t keepLaunches = h->launches;
+    const int keepKind = h->lastKind;
     float ms[2] = { 0.0f, 0.0f };
     const int variants[2] = { ATX_VARIANT_MEGAKERNEL, ATX_VARIANT_WAVEFRONT };
     atx_status st = ATX_OK;
@@ -582,12 +624,22 @@ atx_status atx_calibrate(atx_handle h, uint32_t n_frames, float* megakernel_ms, 
         }
     }
     h->dAccum = keep;
+    h->calibrating = false;
+    h->launches = keepLaunches;
+    h->lastKind = keepKind;
     cudaStreamSynchronize(h->stream);
     cudaFree(scratch);
     h->timed = false;
     if (st != ATX_OK)
         return st;
     h->autoVariant = (ms[1] > 0.0f && ms[1] < ms[0]) ? ATX_VARIANT_WAVEFRONT : ATX_VARIANT_MEGAKERNEL;
+    if (h->autoVariant == ATX_VARIANT_MEGAKERNEL && h->dWave)
+    {
+        // the wavefront scratch (5 float4 + 2 u32 per path) is only worth keeping for the variant that uses it
+        cudaFree(h->dWave);
+        h->dWave = nullptr;
+        h->waveBytes = 0;
+    }
     if (megakernel_ms) *megakernel_ms = ms[0];
     if (wavefront_ms) *wavefront_ms = ms[1];
     return ATX_OK;
@@ -797,7 +849,7 @@ atx_status atx_comm_unique_id(uint8_t id[128])
     if (!id)
         return fail(ATX_ERR_INVALID, "id is null");
     if (!nccl().ok)
-        return fail(ATX_ERR_NCCL, "NCCL library not loadable: %s", dlerror() ? dlerror() : "symbols missing");
+        return fail(ATX_ERR_NCCL, "NCCL library not loadable: %s", nccl().loadError.c_str());
     ncclUniqueId uid;
     ncclResult_t r = nccl().GetUniqueId(&uid);
     if (r != ncclSuccess)

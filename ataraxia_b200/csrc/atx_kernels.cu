@@ -1438,7 +1438,10 @@ cudaError_t configure()
     e = cudaFuncSetAttribute(megakernel_wq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(megakernel_wq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    e = cudaFuncSetAttribute(megakernel_wq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    return configure_wavefront();
 }
 
 cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream_t s)

@@ -26,7 +26,8 @@ constexpr uint32_t kWarpQueueMinFrames = 4;  // frames per launch from which the
                                              // (config 2 geometry, ms per launch, while-while / warp-queue: 1 frame 0.128 / 0.156,
                                              // 2: 0.169 / 0.179, 4: 0.257 / 0.237, 8: 0.428 / 0.324, 32: 1.36 / 1.10, 1024: 31.1 / 22.6)
 
-cudaError_t configure();
+cudaError_t configure();           // per atx_create, after cudaSetDevice: shared-memory opt-in of every kernel on that device
+cudaError_t configure_wavefront(); // (atx_wavefront.cu's share of it)
 int mega_kind(const atxk::RenderParams& p, int requested);
 cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, uint32_t nM, const float* lightAoS,
                        uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);

@@ -201,20 +201,18 @@ uint32_t wavefront_frames_per_wave(uint32_t pixels, uint32_t nFrames)
 
 // One launch worth of frames in waves of `framesPerWave`. `work` is the device scratch of
 // wavefront_bytes(framesPerWave * pixels). Returns the number of kernels launched through *launches.
+// per device (the attribute belongs to the current device's copy of the function): called from configure()
+cudaError_t configure_wavefront()
+{
+    return cudaFuncSetAttribute(wf_bounce, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+}
+
 cudaError_t render_wavefront(const RenderParams& p, void* work, uint32_t framesPerWave, uint64_t* launches, cudaStream_t s)
 {
     const uint32_t P = p.width * p.height;
     const uint32_t capacity = framesPerWave * P;
     if (static_cast<size_t>(p.nSpheres) * sizeof(float4) > static_cast<size_t>(kMaxSmemBytes))
         return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(wf_bounce, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
     WavefrontParams w;
     w.state = static_cast<float4*>(work);
     w.samples = w.state + 4ull * capacity;

@@ -5,6 +5,7 @@
 // throws json::out_of_range / json::type_error: both escape Utils::importScene uncaught.
 #pragma once
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -122,8 +123,10 @@ private:
     {
         while (p < t.size() && (t[p] == ' ' || t[p] == '\t' || t[p] == '\n' || t[p] == '\r')) p++;
     }
-    static Json parseValue(const std::string& t, size_t& p)
+    static constexpr int kMaxDepth = 256; // nesting cap: a hostile file cannot exhaust the stack
+    static Json parseValue(const std::string& t, size_t& p, int depth = 0)
     {
+        if (depth > kMaxDepth) throw std::runtime_error("json: nesting too deep");
         skipWs(t, p);
         if (p >= t.size()) throw std::runtime_error("json: unexpected end of input");
         const char c = t[p];
@@ -141,7 +144,7 @@ private:
                 skipWs(t, p);
                 if (p >= t.size() || t[p] != ':') throw std::runtime_error("json: expected ':'");
                 p++;
-                j.m_obj[key] = parseValue(t, p);
+                j.m_obj[key] = parseValue(t, p, depth + 1);
                 skipWs(t, p);
                 if (p < t.size() && t[p] == ',') { p++; continue; }
                 if (p < t.size() && t[p] == '}') { p++; return j; }
@@ -156,7 +159,7 @@ private:
             if (p < t.size() && t[p] == ']') { p++; return j; }
             while (true)
             {
-                j.m_arr.push_back(parseValue(t, p));
+                j.m_arr.push_back(parseValue(t, p, depth + 1));
                 skipWs(t, p);
                 if (p < t.size() && t[p] == ',') { p++; continue; }
                 if (p < t.size() && t[p] == ']') { p++; return j; }
@@ -167,15 +170,35 @@ private:
         if (t.compare(p, 4, "true") == 0) { p += 4; return Json(true); }
         if (t.compare(p, 5, "false") == 0) { p += 5; return Json(false); }
         if (t.compare(p, 4, "null") == 0) { p += 4; return Json(); }
-        // number: integers without fraction/exponent stay integers (nlohmann keeps them as int64)
-        const char* start = t.c_str() + p;
-        char* end = nullptr;
-        const double d = std::strtod(start, &end);
-        if (end == start) throw std::runtime_error("json: invalid value");
+        // number: the JSON grammar ( -? int frac? exp? ) is checked by hand, the digits go through std::from_chars,
+        // which ignores the process locale (strtod honours LC_NUMERIC and also takes inf/nan/hex/'+'). Integers
+        // without fraction/exponent stay integers (nlohmann keeps them as int64).
+        size_t q = p;
         bool integral = true;
-        for (const char* q = start; q < end; q++)
-            if (*q == '.' || *q == 'e' || *q == 'E') integral = false;
-        p += static_cast<size_t>(end - start);
+        const auto digits = [&]() { const size_t b = q; while (q < t.size() && t[q] >= '0' && t[q] <= '9') q++; return q > b; };
+        if (q < t.size() && t[q] == '-') q++;
+        if (q < t.size() && t[q] == '0') q++;
+        else if (!digits()) throw std::runtime_error("json: invalid value");
+        if (q < t.size() && t[q] == '.')
+        {
+            q++;
+            integral = false;
+            if (!digits()) throw std::runtime_error("json: digits expected after '.'");
+        }
+        if (q < t.size() && (t[q] == 'e' || t[q] == 'E'))
+        {
+            q++;
+            integral = false;
+            if (q < t.size() && (t[q] == '+' || t[q] == '-')) q++;
+            if (!digits()) throw std::runtime_error("json: digits expected in the exponent");
+        }
+        double d = 0.0;
+        const auto res = std::from_chars(t.data() + p, t.data() + q, d);
+        if (res.ec == std::errc::result_out_of_range)
+            d = t[p] == '-' ? -HUGE_VAL : HUGE_VAL; // like strtod
+        else if (res.ec != std::errc() || res.ptr != t.data() + q)
+            throw std::runtime_error("json: invalid number");
+        p = q;
         Json j(d);
         if (integral) j.m_type = Type::Integer;
         return j;
@@ -223,20 +246,21 @@ private:
         if (d == 0.0) { out += std::signbit(d) ? "-0.0" : "0.0"; return; }
         // shortest digit string that round-trips (nlohmann's Grisu2 gives the same digits), laid out
         // like nlohmann: plain decimals for 1e-5 < |d| < 1e15, exponent form outside
-        char buf[48];
-        int prec = 1;
-        for (; prec <= 17; prec++)
-        {
-            std::snprintf(buf, sizeof(buf), "%.*e", prec - 1, d);
-            if (std::strtod(buf, nullptr) == d) break;
-        }
-        const int e10 = static_cast<int>(std::floor(std::log10(std::fabs(d))));
+        // std::to_chars: shortest round-trip digits, independent of the process locale
+        char buf[64];
+        auto r = std::to_chars(buf, buf + sizeof(buf), d, std::chars_format::scientific);
+        std::string sci(buf, r.ptr);
+        const int e10 = std::atoi(sci.c_str() + sci.find('e') + 1);
         if (e10 > -5 && e10 < 15)
         {
-            const int decimals = std::max(prec - 1 - e10, 1);
-            std::snprintf(buf, sizeof(buf), "%.*f", decimals, d);
+            r = std::to_chars(buf, buf + sizeof(buf), d, std::chars_format::fixed);
+            std::string fixed(buf, r.ptr);
+            if (fixed.find('.') == std::string::npos)
+                fixed += ".0";
+            out += fixed;
         }
-        out += buf;
+        else
+            out += sci;
     }
     static void writeString(std::string& out, const std::string& s)
     {
@@ -250,7 +274,18 @@ private:
             case '\n': out += "\\n"; break;
             case '\t': out += "\\t"; break;
             case '\r': out += "\\r"; break;
-            default: out += c; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if (static_cast<unsigned char>(c) < 0x20)
+                {
+                    char u[8];
+                    std::snprintf(u, sizeof(u), "\\u%04x", static_cast<unsigned>(static_cast<unsigned char>(c)));
+                    out += u;
+                }
+                else
+                    out += c;
+                break;
             }
         }
         out += '"';

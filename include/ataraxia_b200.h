@@ -151,7 +151,8 @@ enum {
     ATX_TUNE_PARK_THRESHOLD = 3 /* while-while form: parked hits per warp (1..32) that trigger the
                                    bounce phase (default 8) */,
     ATX_TUNE_CLAIM_THRESHOLD = 4 /* idle lanes per warp (1..32) that trigger a batched claim from the
-                                   pixel pool (default 8) */
+                                   pixel pool; 0 (default) = per form: 32 while-while (whole 8x4
+                                   tiles), 3 warp-queue, 2 two-slot packed */
 };
 ATX_API atx_status atx_set_tuning(atx_handle h, int key, int64_t value);
 
@@ -194,12 +195,12 @@ ATX_API atx_status atx_sync(atx_handle h);
  * call's kernels. Synchronises. */
 ATX_API atx_status atx_last_render_ms(atx_handle h, float* out_ms);
 
-/* General-purpose device timers on the handle's stream (CUDA events), e.g. to bracket
- * render + all-reduce. slot in [0, 8). elapsed synchronises on the later event. */
 /* Megakernel form the last launch used (1 while-while, 2 two-slot packed, 3 warp-queue; 0 before any launch
  * or after a wavefront launch): what ATX_TUNE_MEGA_KIND = 0 resolved to. */
 ATX_API atx_status atx_last_mega_kind(atx_handle h, int* out);
 
+/* General-purpose device timers on the handle's stream (CUDA events), e.g. to bracket
+ * render + all-reduce. slot in [0, 8). elapsed synchronises on the later event. */
 ATX_API atx_status atx_event_record(atx_handle h, int slot);
 ATX_API atx_status atx_event_elapsed_ms(atx_handle h, int slot_begin, int slot_end, float* out_ms);
 

@@ -17,9 +17,18 @@
 //   <prefix>.rgba<k>.u32 W*H    packed image after frame k
 // and prints one JSON line with wall-clock timings of Renderer::Render.
 //
+// Kernel-only time of the reference's kernelRender (BASELINE.md §4 Baseline A (ii)) WITHOUT touching
+// its source: Renderer::Render launches through the runtime entry cudaLaunchKernel and then blocks on
+// cudaDeviceSynchronize (Renderer.cu:223-240). This binary links the SHARED CUDA runtime and defines
+// cudaLaunchKernel itself: the definition below brackets every launch made while a Render() call is in
+// progress with a pair of CUDA events on the launch stream and forwards to the real entry
+// (dlsym(RTLD_NEXT)). Render() launches exactly one kernel per frame, so the event pairs are the
+// per-frame kernelRender times.
+//
 // usage: ref_headless scene.json W H maxBounces skyLight frames prefix [k1,k2,...]
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -37,6 +46,33 @@
 #include "Renderer.h"
 #undef private
 #include "Utils.h"
+
+namespace
+{
+bool g_timeLaunches = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_launchEvents;
+}
+
+extern "C" cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t sharedMem, cudaStream_t stream)
+{
+    using Fn = cudaError_t (*)(const void*, dim3, dim3, void**, size_t, cudaStream_t);
+    static Fn real = reinterpret_cast<Fn>(dlsym(RTLD_NEXT, "cudaLaunchKernel"));
+    if (!real)
+    {
+        std::fprintf(stderr, "ref_headless: the shared CUDA runtime's cudaLaunchKernel was not found\n");
+        std::exit(3);
+    }
+    if (!g_timeLaunches)
+        return real(func, grid, block, args, sharedMem, stream);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, stream);
+    const cudaError_t e = real(func, grid, block, args, sharedMem, stream);
+    cudaEventRecord(b, stream);
+    g_launchEvents.emplace_back(a, b);
+    return e;
+}
 
 __global__ void primaryHitKernel(uint32_t width, uint32_t height, glm::vec3 origin, const glm::vec3* dirs,
     const Sphere* spheres, size_t numSpheres, int* out)
@@ -111,7 +147,9 @@ int main(int argc, char** argv)
     for (int k = 1; k <= frames; k++)
     {
         const auto t0 = std::chrono::steady_clock::now();
+        g_timeLaunches = true;
         r.Render(cam, scene);
+        g_timeLaunches = false;
         const auto t1 = std::chrono::steady_clock::now();
         ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
         if (!quiet && dumpAt.count(k))
@@ -155,15 +193,33 @@ int main(int argc, char** argv)
         cudaFree(d_out);
     }
 
+    // kernel-only: one event pair per launch made inside Render()
+    std::vector<double> kms;
+    for (auto& ev : g_launchEvents)
+    {
+        float v = 0.0f;
+        if (cudaEventElapsedTime(&v, ev.first, ev.second) == cudaSuccess)
+            kms.push_back(v);
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    std::vector<double> ksorted = kms;
+    std::sort(ksorted.begin(), ksorted.end());
+    double ksum = 0.0;
+    for (double v : kms)
+        ksum += v;
+
     std::vector<double> sorted = ms;
     std::sort(sorted.begin(), sorted.end());
     const double total = std::chrono::duration<double, std::milli>(t_all1 - t_all0).count();
     cudaError_t err = cudaGetLastError();
     std::printf("{\"impl\": \"reference-cuda\", \"width\": %u, \"height\": %u, \"frames\": %d, \"max_bounces\": %d, "
         "\"num_spheres\": %zu, \"total_ms\": %.4f, \"first_frame_ms\": %.4f, \"median_frame_ms\": %.4f, "
-        "\"min_frame_ms\": %.4f, \"cuda_error\": \"%s\"}\n",
+        "\"min_frame_ms\": %.4f, \"kernel_launches\": %zu, \"median_kernel_ms\": %.4f, \"min_kernel_ms\": %.4f, "
+        "\"mean_kernel_ms\": %.4f, \"cuda_error\": \"%s\"}\n",
         W, H, frames, bounces, r.m_numSpheres, total, ms.empty() ? 0.0 : ms[0],
         sorted.empty() ? 0.0 : sorted[sorted.size() / 2], sorted.empty() ? 0.0 : sorted[0],
-        cudaGetErrorString(err));
+        kms.size(), ksorted.empty() ? 0.0 : ksorted[ksorted.size() / 2], ksorted.empty() ? 0.0 : ksorted[0],
+        kms.empty() ? 0.0 : ksum / kms.size(), cudaGetErrorString(err));
     return err == cudaSuccess ? 0 : 1;
 }

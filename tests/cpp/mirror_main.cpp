@@ -7,6 +7,7 @@
 //   mirror_main app <scene.json> <out.bin>                          -> the Ataraxia layer: frame-index behaviour of edits
 //   mirror_main image <prefix>                                      -> a test pattern through Image::savePPM / savePNG
 #include <ataraxia/Ataraxia.h>
+#include <clocale>
 #include <cstdio>
 #include <cstdlib>
 
@@ -113,6 +114,29 @@ int main(int argc, char** argv)
                 px[y * W + x] = 0xFF000000u | ((x * 7u) & 0xFFu) | (((y * 23u) & 0xFFu) << 8) | ((((x + y) * 5u) & 0xFFu) << 16);
         Image img(W, H, ImageType::RGBA, px.data());
         return img.savePPM(std::string(argv[2]) + ".ppm") && img.savePNG(std::string(argv[2]) + ".png") ? 0 : 3;
+    }
+    if (mode == "json")
+    {
+        // the JSON reader/writer on its own, under a comma-decimal locale if the host has one (argv[2] = locale name):
+        // numbers are read and written with '.', non-JSON numbers are refused, control characters are escaped,
+        // nesting is capped
+        const bool localeSet = std::setlocale(LC_ALL, argv[2]) != nullptr;
+        int bad = 0;
+        const atx::Json j = atx::Json::parse("{\"a\": [0.5, -1.25e-3, 100, 1e+20, 3.0e-7], \"s\": \"x\\u0001\\b\\fy\"}");
+        bad += j["a"][0].number() != 0.5 || j["a"][1].number() != -1.25e-3 || j["a"][2].getInt() != 100 || j["a"][4].number() != 3.0e-7;
+        const std::string out = j.dump();
+        bad += out != "{\"a\":[0.5,-0.00125,100,1e+20,3e-07],\"s\":\"x\\u0001\\b\\fy\"}";
+        bad += atx::Json::parse(out).dump() != out;
+        for (const char* text : { "inf", "nan", "+1", "0x10", ".5", "1.", "01", "1e", "-", "[1,]" })
+        {
+            try { atx::Json::parse(text); bad++; std::fprintf(stderr, "accepted %s\n", text); }
+            catch (const std::exception&) {}
+        }
+        std::string deep(100000, '[');
+        try { atx::Json::parse(deep); bad++; }
+        catch (const std::exception&) {}
+        std::printf("%d %d %s\n", bad, localeSet ? 1 : 0, out.c_str());
+        return bad ? 4 : 0;
     }
     Scene scene = Utils::importScene(argv[2]);
     if (mode == "cpu")

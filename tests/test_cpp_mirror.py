@@ -49,6 +49,25 @@ def test_example_builds_and_prints_usage(example):
     assert proc.returncode == 2 and "usage:" in proc.stderr
 
 
+def test_json_reader_writer_is_locale_independent_and_strict(driver):
+    """include/ataraxia/Json.h: '.' decimals whatever LC_NUMERIC says (a host application may have called
+    setlocale), JSON number grammar only, control characters escaped, nesting capped."""
+    import locale
+    names = ["C"]
+    for cand in ("de_DE.UTF-8", "de_DE.utf8", "fr_FR.UTF-8", "de_DE"):
+        try:
+            locale.setlocale(locale.LC_NUMERIC, cand)
+            names.append(cand)
+            break
+        except locale.Error:
+            continue
+    locale.setlocale(locale.LC_NUMERIC, "C")
+    for name in names:
+        proc = subprocess.run([str(driver), "json", name], capture_output=True, text=True)
+        assert proc.returncode == 0, (name, proc.stdout, proc.stderr)
+        assert proc.stdout.split()[0] == "0"
+
+
 @pytest.mark.parametrize("file", ["sample_scene.json", "small_scene.json"])
 def test_cpp_host_side_matches_python_mirror(driver, built, tmp_path, file):
     import ataraxia_b200 as atx

@@ -118,21 +118,47 @@ def test_config3_scene_vs_golden(atx, gold):
 
 
 # ---- live runs of the reference CUDA renderer, where the binary travelled to the box ----------------
-def _live_compare(atx, scene_path, W, H, bounces, sky, frames):
+_REF_RUNS = {}
+
+
+def _ref_run(scene_path, W, H, bounces, sky, frames):
+    """One run of the unmodified reference CUDA renderer per (scene, size, settings); several of our kernel
+    forms are compared with the same dump."""
     from oracle import bindings as ob
     if not ob.have_ref_headless():
         pytest.skip("oracle/_ref/ref_headless not present")
+    key = (str(scene_path), W, H, bounces, sky, frames)
+    if key not in _REF_RUNS:
+        _REF_RUNS.clear()                                   # keep one dump in memory
+        _REF_RUNS[key] = ob.run_ref_headless(scene_path, W, H, bounces, sky, frames, dump_at=(1, frames))
+    return _REF_RUNS[key]
+
+
+def _live_compare(atx, scene_path, W, H, bounces, sky, frames, kind=None, variant=None, expect_kind=None, one_launch=False):
+    """Our CUDA path against a live run of the reference's CUDA renderer on the same scene file: ray table,
+    primary hit ids, accumulation after frame 1 and after `frames`, RGBA8 - bit for bit. `kind` forces a
+    megakernel form (ATX_TUNE_MEGA_KIND), `variant` the kernel family, `expect_kind` asserts which form the
+    last launch really used, `one_launch` renders frames 1..n in one launch (instead of 1, then 2..n)."""
+    info, ref = _ref_run(scene_path, W, H, bounces, sky, frames)
     scene = atx.Utils.importScene(str(scene_path))
-    info, ref = ob.run_ref_headless(scene_path, W, H, bounces, sky, frames, dump_at=(1, frames))
     r, cam = setup(atx, scene, W, H, bounces, sky)
+    if kind is not None:
+        r.setTuning(atx.TUNE_MEGA_KIND, kind)
+    if variant is not None:
+        r.variant = variant
     r.uploadScene(scene)
     r.setCamera(cam)
     assert (bits(r.getRayDirections()) == bits(ref["rays"])).all()
     assert (r.getHitIds() == ref["hit"]).all()
-    r.Render(cam, scene)
-    assert (bits(r.getAccumulation()) == bits(ref["acc1"])).all()
-    if frames > 1:
-        r.Render(cam, scene, frames=frames - 1)
+    if one_launch:
+        r.Render(cam, scene, frames=frames)
+    else:
+        r.Render(cam, scene)
+        assert (bits(r.getAccumulation()) == bits(ref["acc1"])).all()
+        if frames > 1:
+            r.Render(cam, scene, frames=frames - 1)
+    if expect_kind is not None:
+        assert r.lastMegaKind() == expect_kind, (r.lastMegaKind(), expect_kind)
     acc = r.getAccumulation()
     assert (bits(acc) == bits(ref[f"acc{frames}"])).all()
     assert (acc[..., 3] == frames).all()
@@ -170,6 +196,49 @@ def test_config3_config4_full_resolution_vs_live_reference(atx, tmp_path, name, 
     _live_compare(atx, p, 3840, 2160, 8, False, frames)
 
 
+def test_live_small_scene_several_lights_every_form(atx, tmp_path):
+    """<= 16 spheres with 3 lights (the `cs` bench workload's scene): the per-bounce light pick
+    PcgHash(seed) % numLights with the un-advanced seed (Renderer.cu:338-340) on the small-scene kernels
+    megakernel_ww<false> (the automatic choice with several lights, at 2 and at 24 frames) and
+    megakernel_wq<false> (forced), each DIRECTLY against the reference CUDA renderer - and the two-slot packed
+    form on the same scene for good measure."""
+    scene = atx.synthetic.small(12, 3, seed=9)
+    p = tmp_path / "cs.json"
+    atx.Utils.exportScene(scene, str(p))
+    _live_compare(atx, p, 240, 136, 8, True, 2, expect_kind=atx.MEGA_WHILE_WHILE)
+    _live_compare(atx, p, 240, 136, 8, True, 24, expect_kind=atx.MEGA_WHILE_WHILE)
+    _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE)
+    _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE, one_launch=True)
+    _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_PAIR, expect_kind=atx.MEGA_PAIR)
+    scene2 = atx.synthetic.small(5, 2, seed=3)
+    p2 = tmp_path / "cs2.json"
+    atx.Utils.exportScene(scene2, str(p2))
+    _live_compare(atx, p2, 97, 55, 6, False, 9, expect_kind=atx.MEGA_WHILE_WHILE)
+    _live_compare(atx, p2, 97, 55, 6, False, 9, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE, one_launch=True)
+
+
+def test_live_natural_chunked_staging(atx, tmp_path):
+    """More spheres than the resident shared-memory budget (> 4608): the double-buffered TMA chunk walk
+    (megakernel_pair<true>) as the automatic plan picks it, against the reference's brute-force kernel on the
+    same 16384-sphere file (small image: the reference needs ~50 ms per frame here)."""
+    scene = atx.synthetic.stress16k()
+    p = tmp_path / "c16k.json"
+    atx.Utils.exportScene(scene, str(p))
+    _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR)
+    _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR, one_launch=True)
+
+
+def test_live_wavefront_variant(atx, tmp_path):
+    """The wavefront variant (per-bounce launches, ray compaction, path records in HBM) directly against the
+    reference CUDA renderer: sample scene (1 light), a 12-sphere / 3-light scene and a 40-sphere / 5-light one."""
+    _live_compare(atx, GOLDEN / "sample_scene.json", 320, 180, 8, False, 6, variant=atx.VARIANT_WAVEFRONT)
+    for i, scene in enumerate([atx.synthetic.small(12, 3, seed=9), atx.synthetic.small(40, 5, seed=11)]):
+        p = tmp_path / f"wf{i}.json"
+        atx.Utils.exportScene(scene, str(p))
+        _live_compare(atx, p, 200, 120, 8, i == 0, 4, variant=atx.VARIANT_WAVEFRONT)
+        _live_compare(atx, p, 200, 120, 8, i == 0, 4, variant=atx.VARIANT_WAVEFRONT, one_launch=True)
+
+
 def test_live_edge_scenes(atx, tmp_path):
     """No lights / out-of-range material index / single sphere — the reference's own edge behaviour."""
     scene = atx.synthetic.small(6, 0, seed=5)                       # no lights: NEE block skipped (Renderer.cu:338)
@@ -200,7 +269,10 @@ def test_vs_cpu_oracle_port(atx, port):
     acc_gpu = r.getAccumulation()
     assert (acc_gpu[..., 3] == acc_cpu[..., 3]).all()                # sample counts exact
     rel = np.abs(acc_gpu[..., :3] - acc_cpu[..., :3]) / np.maximum(np.abs(acc_cpu[..., :3]), 1e-3)
-    assert (rel.max(-1) > RADIANCE_RTOL).mean() <= CHAOTIC_FRACTION
+    outside = float((rel.max(-1) > RADIANCE_RTOL).mean())
+    print(f"vs CPU oracle port: {outside:.5%} of pixels outside rtol {RADIANCE_RTOL} (bound {CHAOTIC_FRACTION:.0%}); "
+          f"hit-id mismatches {(hits_cpu != hits_gpu).mean():.5%}")
+    assert outside <= CHAOTIC_FRACTION
     assert abs(acc_gpu[..., :3].mean() - acc_cpu[..., :3].mean()) / acc_cpu[..., :3].mean() < 1e-3
     r.close()
 
