@@ -141,7 +141,7 @@ struct atx_renderer
 
     // scene
     float *dSphAoS = nullptr, *dMatAoS = nullptr, *dLightAoS = nullptr;
-    float4 *dSpheres = nullptr, *dMats = nullptr, *dLights = nullptr;
+    float4 *dSpheres = nullptr, *dSphFilter = nullptr, *dMats = nullptr, *dLights = nullptr;
     int32_t* dSphMat = nullptr;
     size_t capS = 0, capM = 0, capL = 0;
     uint32_t nS = 0, nM = 0, nL = 0;
@@ -182,6 +182,7 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
     p.nMaterials = h->nM;
     p.nLights = h->nL;
     p.spheres = h->dSpheres;
+    p.sphFilter = h->dSphFilter;
     p.sphMat = h->dSphMat;
     p.mats = h->dMats;
     p.lights = h->dLights;
@@ -287,7 +288,7 @@ atx_status atx_destroy(atx_handle h)
         nccl().CommDestroy(h->comm);
     cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
-    cudaFree(h->dSpheres); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
+    cudaFree(h->dSpheres); cudaFree(h->dSphFilter); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
     for (cudaEvent_t e : h->evUser)
         if (e)
@@ -359,6 +360,7 @@ atx_status atx_upload_scene(atx_handle h, const atx_sphere* spheres, size_t n_sp
     size_t c;
     c = h->capS; if (atx_status s = grow(h->dSphAoS, c, n_spheres, 5)) return s;
     c = h->capS; if (atx_status s = grow(h->dSphMat, c, n_spheres, 1)) return s;
+    c = h->capS; if (atx_status s = grow(h->dSphFilter, c, n_spheres, 1)) return s;
     if (atx_status s = grow(h->dSpheres, h->capS, n_spheres, 1)) return s;
     c = h->capM; if (atx_status s = grow(h->dMatAoS, c, n_materials, 13)) return s;
     if (atx_status s = grow(h->dMats, h->capM, n_materials, atxk::kMatStride)) return s;
@@ -373,7 +375,7 @@ atx_status atx_upload_scene(atx_handle h, const atx_sphere* spheres, size_t n_sp
     h->nS = static_cast<uint32_t>(n_spheres);
     h->nM = static_cast<uint32_t>(n_materials);
     h->nL = static_cast<uint32_t>(n_lights);
-    ATX_CUDA(atx_launch::pack_scene(h->dSphAoS, h->nS, h->dMatAoS, h->nM, h->dLightAoS, h->nL, h->dSpheres, h->dSphMat,
+    ATX_CUDA(atx_launch::pack_scene(h->dSphAoS, h->nS, h->dMatAoS, h->nM, h->dLightAoS, h->nL, h->dSpheres, h->dSphFilter, h->dSphMat,
                                     h->dMats, h->dLights, h->stream));
     h->launches++;
     // the caller's arrays may be pageable: the copies above must have consumed them before we return

@@ -10,9 +10,10 @@ namespace atxk
 
 // ---------------------------------------------------------------------------
 // Scene records in HBM, written once per upload by pack_scene_kernel.
-//   spheres : float4 (-cx, -cy, -cz, radius) one LDS.128 per test. The centre is stored
-//                                           NEGATED: o - c == o + (-c) bit for bit, and the
-//                                           packed f32x2 ops have add but no subtract form
+//   spheres : float4 (-cx, -cy, -cz, radius) the exact test and the hit record. The centre is
+//                                           stored NEGATED: o - c == o + (-c) bit for bit
+//   sphFilter: float4 (-cx, -cy, -cz, kk)   one LDS.128 per packed filter step (two rays);
+//                                           kk = |c|^2 - r^2 - 2^-17 (|c|^2 + r^2), formed in double
 //   sphMat  : int32 material index          read only for the winning sphere
 //   mats    : 6 x float4 per material       everything the shading needs, including the
 //                                           per-material subexpressions the reference
@@ -55,7 +56,8 @@ struct RenderParams
     uint32_t claimThreshold; // idle lanes (of 32) that trigger a batched pixel claim
     uint32_t poolSize;      // pixel ids in the pool: 8x4 tiles x 32, padded tiles included
     uint32_t* pool;         // next unclaimed id (zeroed before the launch)
-    const float4* spheres;
+    const float4* spheres;    // (-cx, -cy, -cz, r): the exact tests, hit records
+    const float4* sphFilter;  // (-cx, -cy, -cz, |c|^2 - r^2 - margin): the packed line filter (filter_sphere)
     const int32_t* sphMat;
     const float4* mats;
     const float4* lights;
@@ -187,50 +189,66 @@ ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, fl
 // Packed filter: TWO rays (the two path slots of a thread) against one sphere per step,
 // every op an f32x2 instruction with the sphere as the broadcast operand.
 //
-//   oc  = o + (-c)                               3 FADD2
-//   hb  = fma(oc.z,d.z, fma(oc.x,d.x, oc.y*d.y))  FMUL2 + 2 FFMA2
-//   q   = fma(oc.z,oc.z, fma(oc.x,oc.x, oc.y^2))  FMUL2 + 2 FFMA2
-//   cc  = fma(-r, r, q)                          2 scalar FFMA (FFMA2 has no negate modifier)
-//   m   = fma(cc, -a, 2^-100)                    FFMA2
-//   pre = fma(hb, hb, m)                         FFMA2
-//   mask = (mask << 1) | signbit(pre)            2 SHF   (ALU pipe)
+// The filter only has to be CONSERVATIVE: a sphere it rejects must be one the reference
+// skips ("disc < 0", Renderer.cu:267); everything it keeps is re-decided by exact_test with
+// the reference's literal sequence, in ascending index order, so (tmin, closest) is exactly
+// Renderer::traceRay's whatever the filter lets through. That freedom is used to take the
+// ray origin out of the per-sphere work. With o.d, o.o and 2o formed once per ray,
 //
-// = 1 LDS.128 + 11 packed + 2 scalar FP + 2 ALU = 16 instructions for two tests. A packed op
-// holds the issue port of its sub-partition for two cycles (tools/ubench_fp32.cu), so the group
-// costs 27 issue cycles per sphere for two rays in theory, 29.9 measured in isolation
-// (tools/ubench_filter.cu): 0.635 of FP32 peak is the ceiling of this loop (19 algorithmic
-// flop per 14.95 cycles x 2 flop/cycle/lane).
+//   disc/4 = (oc.d)^2 - a (oc.oc - r^2),  oc = o - c
+//          = (o.d - c.d)^2 - a (|c|^2 - r^2 - 2 o.c) - a |o|^2
 //
-// A set sign bit proves the reference finds no hit on this sphere: the line misses it. hb and
-// cc are bit-identical to the scalar sequence and pre >= fma(hb,hb,-(a*cc)); the +2^-100 only
-// matters when |a*cc| < 2^-76, where it keeps the -0/flush cases of the reference's
-// disc = fma(b,b,-(4a*cc)) on the candidate side. pre < 0 (not -0) implies disc < 0
-// (Renderer.cu:267). A NaN pre has a clear sign bit (the device's canonical NaN), so it
-// stays a candidate.
-// (Also rejecting "hb >= 0" - sphere behind the origin - with min(pre, -hb) halves the
-// candidates but costs two more ALU instructions per sphere; measured 3 % slower at 4096
-// spheres, so it is not done.)
-// A clear bit makes the sphere a candidate; candidates are re-decided by exact_test in
-// ascending index order, so (tmin, closest) is exactly Renderer::traceRay's.
+//   hb' = fma(-cz,dz, fma(-cx,dx, fma(-cy,dy, o.d)))          3 FFMA2
+//   t   = fma(-cz,2oz, fma(-cx,2ox, fma(-cy,2oy, kk)))        3 FFMA2   kk = |c|^2 - r^2 - margin_sphere (per sphere, from the pack kernel)
+//   w   = fma(t, -a, g)                                       1 FFMA2   g  = -a |o|^2 + margin_ray        (per ray)
+//   pre = fma(hb', hb', w)                                    1 FFMA2
+//   mask = (mask << 1) | signbit(pre)                         2 SHF     (ALU pipe)
+//
+// = 1 LDS.128 + 8 packed FP + 2 ALU = 11 instructions for two tests, 19 issue cycles (a packed op
+// holds the issue port of its sub-partition for two cycles, tools/ubench_fp32.cu) against 27 for
+// the form that follows the reference op by op (3 FADD2 for oc, 6 for the two dot products, 2 FFMA
+// for -r*r, 2 FFMA2): the reference's 19 algorithmic flop per test are decided with 16.
+//
+// Rounding. This chain cancels |c|^2 + |o|^2 - 2 o.c instead of forming o - c first, so its
+// absolute error grows with |o|^2 + |c|^2 (times a) instead of |o - c|^2. With u = 2^-24, worst case over
+// both chains (the reference's own rounding included, since it is ITS computed disc that decides):
+//   | pre - disc_ref/4 |  <=  u a (78 |o|^2 + 80 |c|^2 + 15 r^2)        (derivation: DESIGN.md section 3.2)
+// The margins make the test one-sided by more than that: margin_sphere = 2^-17 (|c|^2 + r^2) and
+// margin_ray = 2^-17 a |o|^2 (+ 2^-100 for flush-to-zero corner cases): 128 u each. A set sign bit
+// therefore proves disc_ref < 0. The price is a sphere radius that looks larger by
+// 2^-18 (|o|^2 + |c|^2) / r^2 relative: +0.6 % candidates on the config-3 scene, +2.5 % on config 4
+// (measured, tests/test_filter_margin.py, which also searches for false negatives with grazing rays:
+// none at 2^-20, the first at 2^-22).
+// A NaN pre has a clear sign bit (the device's canonical NaN), so it stays a candidate; the pack kernel
+// replaces a non-finite kk by -FLT_MAX (always a candidate).
 // ---------------------------------------------------------------------------
+constexpr float kFilterMargin = 7.62939453125e-06f; // 2^-17
+
 struct RayPair
 {
-    f32x2 ox, oy, oz, dx, dy, dz;
-    f32x2 na; // (-a0, -a1), a = dot(d,d)
+    f32x2 dx, dy, dz;     // direction
+    f32x2 o2x, o2y, o2z;  // 2 * origin
+    f32x2 od;             // o . d
+    f32x2 na;             // -a, a = d . d
+    f32x2 g;              // -a |o|^2 + 2^-17 a |o|^2 + 2^-100
 };
 
+ATX_DEV void ray_pair_lane(float ox, float oy, float oz, float dx, float dy, float dz, float a, float& od, float& g)
+{
+    od = fdot3(ox, oy, oz, dx, dy, dz);
+    const float oo = fdot3(ox, oy, oz, ox, oy, oz);
+    const float mray = fmul(a, fmul(oo, kFilterMargin));
+    g = fadd(ffma(fneg(a), oo, mray), 7.888609052210118e-31f); // + 2^-100
+}
+
+// sp = (-cx, -cy, -cz, kk)
 ATX_DEV void filter_sphere(const float4 sp, const RayPair& r, uint32_t& m0, uint32_t& m1)
 {
-    const f32x2 ocx = fadd2(r.ox, pk2(sp.x, sp.x));
-    const f32x2 ocy = fadd2(r.oy, pk2(sp.y, sp.y));
-    const f32x2 ocz = fadd2(r.oz, pk2(sp.z, sp.z));
-    const f32x2 hb = ffma2(ocz, r.dz, ffma2(ocx, r.dx, fmul2(ocy, r.dy)));
-    const f32x2 q = ffma2(ocz, ocz, ffma2(ocx, ocx, fmul2(ocy, ocy)));
-    const float nr = fneg(sp.w);
-    const f32x2 cc = pk2(ffma(nr, sp.w, lo2(q)), ffma(nr, sp.w, hi2(q)));
-    const float tiny = 7.888609052210118e-31f; // 2^-100
-    const f32x2 m = ffma2(cc, r.na, pk2(tiny, tiny));
-    const f32x2 pre = ffma2(hb, hb, m);
+    const f32x2 cx = pk2(sp.x, sp.x), cy = pk2(sp.y, sp.y), cz = pk2(sp.z, sp.z);
+    const f32x2 hb = ffma2(cz, r.dz, ffma2(cx, r.dx, ffma2(cy, r.dy, r.od)));
+    const f32x2 t = ffma2(cz, r.o2z, ffma2(cx, r.o2x, ffma2(cy, r.o2y, pk2(sp.w, sp.w))));
+    const f32x2 w = ffma2(t, r.na, r.g);
+    const f32x2 pre = ffma2(hb, hb, w);
     m0 = shift_in_sign(m0, lo2(pre));
     m1 = shift_in_sign(m1, hi2(pre));
 }

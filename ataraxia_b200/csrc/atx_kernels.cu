@@ -28,7 +28,7 @@ __device__ __forceinline__ float flip_sign(float v) { return __uint_as_float(__f
 __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSpheres,
                                   const float* __restrict__ matAoS, uint32_t nMaterials,
                                   const float* __restrict__ lightAoS, uint32_t nLights,
-                                  float4* __restrict__ spheres, int32_t* __restrict__ sphMat,
+                                  float4* __restrict__ spheres, float4* __restrict__ sphFilter, int32_t* __restrict__ sphMat,
                                   float4* __restrict__ mats, float4* __restrict__ lights)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,6 +38,13 @@ __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSp
         const float r = s[3];
         // centre stored negated (pure sign flip): o - c == o + (-c) bit for bit
         spheres[i] = make_float4(flip_sign(s[0]), flip_sign(s[1]), flip_sign(s[2]), r);
+        // the line filter's constant (filter_sphere): |c|^2 - r^2 less the one-sided margin, one rounding
+        const double c2 = double(s[0]) * double(s[0]) + double(s[1]) * double(s[1]) + double(s[2]) * double(s[2]);
+        const double r2 = double(r) * double(r);
+        float kk = static_cast<float>(c2 - r2 - double(kFilterMargin) * (c2 + r2));
+        if (!(fabsf(kk) <= 3.402823466e+38f))
+            kk = -3.402823466e+38f; // overflow or NaN in the inputs: always a candidate, the exact test decides
+        sphFilter[i] = make_float4(flip_sign(s[0]), flip_sign(s[1]), flip_sign(s[2]), kk);
         int32_t id = reinterpret_cast<const int32_t*>(s)[4];
         if (static_cast<uint32_t>(id) >= nMaterials) // Renderer.cu:30-37
             id = 0;
@@ -127,8 +134,9 @@ __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, u
         intersect_sphere(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
 }
 
-// packed: the two rays of a thread against spheres [0, count) resident at `sph` (padded to a
-// multiple of 8). Two stages per super-block of up to kSuperBlock spheres:
+// packed: the two rays of a thread against the filter records of spheres [0, count) resident at `sph`
+// (shared memory, padded to a multiple of 8); `exact` is the global array of exact records (indexed from
+// base: the few candidates of a lane are read through L1). Two stages per super-block of up to kSuperBlock spheres:
 //   filter   blocks of 32 spheres, branch-free: two 32-bit candidate words per block go to this
 //            thread's private column of `cand` (shared memory, conflict-free), plus one bit per
 //            block in a "non-empty" word per slot;
@@ -145,7 +153,7 @@ __host__ __device__ __forceinline__ uint32_t cand_words(const RenderParams& p)
     return 2u * ((span + 31u) / 32u);
 }
 
-__device__ __forceinline__ void trace_range2(const float4* sph, uint32_t count, uint32_t base, uint32_t* cand,
+__device__ __forceinline__ void trace_range2(const float4* sph, const float4* __restrict__ exact, uint32_t count, uint32_t base, uint32_t* cand,
                                              const RayPair& rp, const PathState& s0, const PathState& s1,
                                              bool live0, bool live1, const RayConst& k0, const RayConst& k1,
                                              float& tmin0, int& closest0, float& tmin1, int& closest1)
@@ -210,14 +218,14 @@ __device__ __forceinline__ void trace_range2(const float4* sph, uint32_t count, 
                 const uint32_t i = __clz(cur0);
                 cur0 &= ~(0x80000000u >> i);
                 const uint32_t idx = sb + b0 * 32u + i;
-                exact_test(sph[idx], static_cast<int>(base + idx), s0.ox, s0.oy, s0.oz, s0.dx, s0.dy, s0.dz, k0, tmin0, closest0);
+                exact_test(__ldg(exact + base + idx), static_cast<int>(base + idx), s0.ox, s0.oy, s0.oz, s0.dx, s0.dy, s0.dz, k0, tmin0, closest0);
             }
             if (cur1)
             {
                 const uint32_t i = __clz(cur1);
                 cur1 &= ~(0x80000000u >> i);
                 const uint32_t idx = sb + b1 * 32u + i;
-                exact_test(sph[idx], static_cast<int>(base + idx), s1.ox, s1.oy, s1.oz, s1.dx, s1.dy, s1.dz, k1, tmin1, closest1);
+                exact_test(__ldg(exact + base + idx), static_cast<int>(base + idx), s1.ox, s1.oy, s1.oz, s1.dx, s1.dy, s1.dz, k1, tmin1, closest1);
             }
         }
     }
@@ -1123,7 +1131,7 @@ __device__ __forceinline__ void slot_claim(const RenderParams& p, Slot& t, uint3
 template <bool kChunked>
 __device__ __forceinline__ void slot_resume(const RenderParams& p, Slot& t, const float4* sphS, uint32_t& rays, uint32_t& paths)
 {
-    const float4 sp = kChunked ? __ldg(p.spheres + t.cPrimary) : sphS[t.cPrimary];
+    const float4 sp = __ldg(p.spheres + t.cPrimary); // shared memory holds the filter records; the exact record comes through L1
     while (true)
     {
         if (t.j >= p.nFrames)
@@ -1188,7 +1196,7 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
             slot_finish<kChunked>(p, t, sphS, rays, paths);
             return;
         }
-        const float4 sp = kChunked ? __ldg(p.spheres + closest) : sphS[closest];
+        const float4 sp = __ldg(p.spheres + closest);
         if (path_hit(p, t.s, sp, closest, tmin))
             t.shadow = true;
         else
@@ -1214,12 +1222,19 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
     const RayConst k0 = ray_constants(a.s.dx, a.s.dy, a.s.dz);
     const RayConst k1 = ray_constants(b.s.dx, b.s.dy, b.s.dz);
     RayPair rp;
-    rp.ox = pk2(a.s.ox, b.s.ox); rp.oy = pk2(a.s.oy, b.s.oy); rp.oz = pk2(a.s.oz, b.s.oz);
+    float od0, od1, g0, g1;
+    ray_pair_lane(a.s.ox, a.s.oy, a.s.oz, a.s.dx, a.s.dy, a.s.dz, k0.a, od0, g0);
+    ray_pair_lane(b.s.ox, b.s.oy, b.s.oz, b.s.dx, b.s.dy, b.s.dz, k1.a, od1, g1);
     rp.dx = pk2(a.s.dx, b.s.dx); rp.dy = pk2(a.s.dy, b.s.dy); rp.dz = pk2(a.s.dz, b.s.dz);
+    rp.o2x = pk2(fadd(a.s.ox, a.s.ox), fadd(b.s.ox, b.s.ox));
+    rp.o2y = pk2(fadd(a.s.oy, a.s.oy), fadd(b.s.oy, b.s.oy));
+    rp.o2z = pk2(fadd(a.s.oz, a.s.oz), fadd(b.s.oz, b.s.oz));
+    rp.od = pk2(od0, od1);
     rp.na = pk2(fneg(k0.a), fneg(k1.a));
+    rp.g = pk2(g0, g1);
     if (!kChunked)
     {
-        trace_range2(sphS, p.nSpheres, 0u, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
+        trace_range2(sphS, p.spheres, p.nSpheres, 0u, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
     }
     else
     {
@@ -1230,16 +1245,16 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
         const uint32_t nChunks = (p.nSpheres + C - 1) / C;
         float4* buf = const_cast<float4*>(sphS);
         if (threadIdx.x == 0)
-            bulk_load(buf, p.spheres, min(C, p.nSpheres) * 16u, &mbar[0]);
+            bulk_load(buf, p.sphFilter, min(C, p.nSpheres) * 16u, &mbar[0]);
         for (uint32_t c = 0; c < nChunks; c++)
         {
             const uint32_t cur = c & 1u;
             if (c + 1 < nChunks && threadIdx.x == 0)
-                bulk_load(buf + (cur ^ 1u) * stride, p.spheres + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C) * 16u, &mbar[cur ^ 1u]);
+                bulk_load(buf + (cur ^ 1u) * stride, p.sphFilter + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C) * 16u, &mbar[cur ^ 1u]);
             mbar_wait(&mbar[cur], (phase >> cur) & 1u); // chunk c has landed
             phase ^= 1u << cur;
             if (a.alive || b.alive)
-                trace_range2(buf + cur * stride, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
+                trace_range2(buf + cur * stride, p.spheres, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
                              tmin0, closest0, tmin1, closest1);
             __syncthreads();
         }
@@ -1257,7 +1272,7 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
     uint32_t phase = 0u; // parity of the next completion of each mbarrier
 
     if (!kChunked)
-        stage_spheres(sphS, p.spheres, p.nSpheres);
+        stage_spheres(sphS, p.sphFilter, p.nSpheres);
     else
     {
         // the padded tail of a buffer is masked out of the candidate set, never tested; zero it once so
@@ -1382,12 +1397,12 @@ using namespace atxk;
 static dim3 tile_grid(uint32_t w, uint32_t h) { return dim3((w + 31u) / 32u, (h + 7u) / 8u); }
 
 cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, uint32_t nM, const float* lightAoS,
-                       uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s)
+                       uint32_t nL, float4* spheres, float4* sphFilter, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s)
 {
     const uint32_t n = max(nS, max(nM, nL));
     if (n == 0)
         return cudaSuccess;
-    pack_scene_kernel<<<(n + 255) / 256, 256, 0, s>>>(sphAoS, nS, matAoS, nM, lightAoS, nL, spheres, sphMat, mats, lights);
+    pack_scene_kernel<<<(n + 255) / 256, 256, 0, s>>>(sphAoS, nS, matAoS, nM, lightAoS, nL, spheres, sphFilter, sphMat, mats, lights);
     return cudaGetLastError();
 }
 

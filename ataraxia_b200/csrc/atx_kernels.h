@@ -30,7 +30,7 @@ cudaError_t configure();           // per atx_create, after cudaSetDevice: share
 cudaError_t configure_wavefront(); // (atx_wavefront.cu's share of it)
 int mega_kind(const atxk::RenderParams& p, int requested);
 cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, uint32_t nM, const float* lightAoS,
-                       uint32_t nL, float4* spheres, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);
+                       uint32_t nL, float4* spheres, float4* sphFilter, int32_t* sphMat, float4* mats, float4* lights, cudaStream_t s);
 size_t megakernel_smem_bytes(const atxk::RenderParams& p);
 cudaError_t render_mega(const atxk::RenderParams& p, int kind, int smCount, cudaStream_t s);
 // wavefront variant (atx_wavefront.cu)
