@@ -264,11 +264,25 @@ def have_ref_headless() -> bool:
     return REF_HEADLESS.exists()
 
 
-def run_ref_headless(scene_json, W, H, bounces, sky, frames, dump_at=(), timeout=600):
+REF_HEADLESS_SHIM = HERE / "_ref" / "ref_headless_shim"
+
+
+def have_dropin_shim() -> bool:
+    return REF_HEADLESS_SHIM.exists()
+
+
+def run_dropin_shim(scene_json, W, H, bounces, sky, frames, dump_at=(), timeout=600):
+    """Run oracle/_ref/ref_headless_shim: the reference application's protocol and its own Camera/SceneNode/Utils
+    objects, with examples/dropin/Renderer.cpp (the product behind the reference's unmodified Renderer.h) in place
+    of Renderer.cu. Same arguments and dump files as run_ref_headless (no rays/hit dumps)."""
+    return run_ref_headless(scene_json, W, H, bounces, sky, frames, dump_at, timeout, exe=REF_HEADLESS_SHIM, extras=False)
+
+
+def run_ref_headless(scene_json, W, H, bounces, sky, frames, dump_at=(), timeout=600, exe=None, extras=True):
     """Run the reference's CUDA renderer (needs a GPU). Returns (info, {name: ndarray})."""
     with tempfile.TemporaryDirectory() as td:
         prefix = str(Path(td) / "ref") if dump_at else "-"
-        cmd = [str(REF_HEADLESS), str(scene_json), str(W), str(H), str(bounces), str(int(sky)), str(frames), prefix]
+        cmd = [str(exe or REF_HEADLESS), str(scene_json), str(W), str(H), str(bounces), str(int(sky)), str(frames), prefix]
         if dump_at:
             cmd.append(",".join(str(k) for k in dump_at))
         proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
@@ -277,9 +291,10 @@ def run_ref_headless(scene_json, W, H, bounces, sky, frames, dump_at=(), timeout
         info = json.loads(proc.stdout.strip().splitlines()[-1])
         out = {}
         if dump_at:
-            out["rays"] = np.fromfile(prefix + ".rays.f32", np.float32).reshape(H, W, 3)
-            out["hit"] = np.fromfile(prefix + ".hit.i32", np.int32).reshape(H, W)
-            out["spheres"] = np.fromfile(prefix + ".spheres.f32", np.float32).reshape(-1, 5)
+            if extras:
+                out["rays"] = np.fromfile(prefix + ".rays.f32", np.float32).reshape(H, W, 3)
+                out["hit"] = np.fromfile(prefix + ".hit.i32", np.int32).reshape(H, W)
+                out["spheres"] = np.fromfile(prefix + ".spheres.f32", np.float32).reshape(-1, 5)
             for k in dump_at:
                 out[f"acc{k}"] = np.fromfile(prefix + f".acc{k}.f32", np.float32).reshape(H, W, 4)
                 out[f"rgba{k}"] = np.fromfile(prefix + f".rgba{k}.u32", np.uint32).reshape(H, W)
