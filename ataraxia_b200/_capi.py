@@ -32,7 +32,7 @@ ATX_OK = 0
 ATX_ERR_INVALID, ATX_ERR_CUDA, ATX_ERR_NCCL, ATX_ERR_NO_DEVICE, ATX_ERR_ALLOC = -1, -2, -3, -4, -5
 VARIANT_AUTO, VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1, 2
 TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD = 1, 2, 3, 4
-MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR, MEGA_WARP_QUEUE = 0, 1, 2, 3
+MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR, MEGA_WARP_QUEUE, MEGA_PAIR_LOCKSTEP = 0, 1, 2, 3, 4
 
 # numpy views of the reference PODs (SceneNode.h:11-21, Scene.h:17-47)
 SPHERE_DTYPE = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("material", "<i4")])

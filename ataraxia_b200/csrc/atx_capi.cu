@@ -438,8 +438,8 @@ atx_status atx_set_tuning(atx_handle h, int key, int64_t value)
         h->chunkOverride = static_cast<uint32_t>(value);
         return ATX_OK;
     case ATX_TUNE_MEGA_KIND:
-        if (value < 0 || value > 3)
-            return fail(ATX_ERR_INVALID, "mega_kind must be 0 (auto), 1 (while-while), 2 (two-slot packed) or 3 (warp-queue)");
+        if (value < 0 || value > 4)
+            return fail(ATX_ERR_INVALID, "mega_kind must be 0 (auto), 1 (while-while), 2 (two-slot packed), 3 (warp-queue) or 4 (two-slot packed, lockstep)");
         h->megaKind = static_cast<int>(value);
         return ATX_OK;
     case ATX_TUNE_PARK_THRESHOLD:

@@ -1083,8 +1083,9 @@ struct Slot
     uint32_t j;      // frames done
     uint32_t frame;
     bool alive;
-    bool shadow;     // the ray in flight is a shadow ray
+    bool shadow;     // free-running form: the ray in flight is a shadow ray
     bool fresh;      // the ray in flight is the pixel's primary ray
+    bool ray;        // lockstep form: the slot has a ray for the coming trace
 };
 
 __device__ __forceinline__ void slot_retire(const RenderParams& p, Slot& t, uint32_t& paths)
@@ -1123,6 +1124,7 @@ __device__ __forceinline__ void slot_claim(const RenderParams& p, Slot& t, uint3
     t.alive = true;
     t.fresh = true;
     t.shadow = false;
+    t.ray = true;
 }
 
 // Start frame t.frame's path from the cached primary hit and run it up to its next trace:
@@ -1215,7 +1217,8 @@ __device__ __forceinline__ void slot_advance(const RenderParams& p, Slot& t, con
 // one ray per slot against the whole scene
 template <bool kChunked>
 __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* sphS, uint32_t* candS, uint64_t* mbar, uint32_t& phase,
-                                           const Slot& a, const Slot& b, float& tmin0, int& closest0, float& tmin1, int& closest1)
+                                           const Slot& a, const Slot& b, bool live0, bool live1, float& tmin0, int& closest0, float& tmin1,
+                                           int& closest1)
 {
     tmin0 = tmin1 = 3.402823466e+38f; // FLT_MAX
     closest0 = closest1 = -1;
@@ -1234,7 +1237,7 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
     rp.g = pk2(g0, g1);
     if (!kChunked)
     {
-        trace_range2(sphS, p.spheres, p.nSpheres, 0u, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1, tmin0, closest0, tmin1, closest1);
+        trace_range2(sphS, p.spheres, p.nSpheres, 0u, candS, rp, a.s, b.s, live0, live1, k0, k1, tmin0, closest0, tmin1, closest1);
     }
     else
     {
@@ -1253,8 +1256,8 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
                 bulk_load(buf + (cur ^ 1u) * stride, p.sphFilter + (c + 1) * C, min(C, p.nSpheres - (c + 1) * C) * 16u, &mbar[cur ^ 1u]);
             mbar_wait(&mbar[cur], (phase >> cur) & 1u); // chunk c has landed
             phase ^= 1u << cur;
-            if (a.alive || b.alive)
-                trace_range2(buf + cur * stride, p.spheres, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, a.alive, b.alive, k0, k1,
+            if (live0 || live1)
+                trace_range2(buf + cur * stride, p.spheres, min(C, p.nSpheres - c * C), c * C, candS, rp, a.s, b.s, live0, live1, k0, k1,
                              tmin0, closest0, tmin1, closest1);
             __syncthreads();
         }
@@ -1332,7 +1335,7 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
         // ---- trace the ray in flight of each slot against every sphere (Renderer::traceRay) ----
         float tmin0, tmin1;
         int closest0, closest1;
-        trace_pair<kChunked>(p, sphS, candS, mbar, phase, a, b, tmin0, closest0, tmin1, closest1);
+        trace_pair<kChunked>(p, sphS, candS, mbar, phase, a, b, a.alive, b.alive, tmin0, closest0, tmin1, closest1);
         if (a.alive)
         {
             traced++;
@@ -1343,6 +1346,188 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
             traced++;
             slot_advance<kChunked>(p, b, sphS, closest1, tmin1, rays, paths);
         }
+    }
+    count_rays(p, rays, traced, paths);
+}
+
+// ---------------------------------------------------------------------------
+// Megakernel, two-slot packed form in LOCKSTEP (large scenes, several frames per launch).
+//
+// In the free-running form above a slot traces whatever ray its path needs next, so after a while half the
+// slots of a warp come back from a trace with a shadow-ray result (Cook-Torrance, roulette, next direction) and
+// half with a closest-hit result (hit record, light pick): the code between two traces ran 6-14 lanes wide and
+// was 20 % of all executed instructions on config 3 (profiles/r02a_ncu_full_megakernel_c3.txt). Here every
+// iteration of the CTA makes the SAME two traces in the same order:
+//   C  closest-hit rays of all slots (a newly claimed pixel's primary ray is one of them); then, for every slot
+//      at once: a miss ends the path, adds the sample and restarts from the cached primary hit - and that
+//      restart and a hit both continue with path_hit (hit record, emission, light pick), so the whole warp runs it
+//      together;
+//   S  shadow rays of all slots; then path_shadow + path_bounce for every slot at once.
+// A path that ends in S (roulette, bounce limit: a few per cent of the paths) has no ray for the next C trace:
+// its slot sits that one trace out and restarts with everybody else's path_hit. A newly claimed pixel waits at
+// most one S trace for its primary ray. Everything else (pixel pool, packed filter + exact replay, sample order)
+// is the free-running form's, and so are the results, bit for bit. Launches of fewer than kLockstepMinFrames
+// frames keep the free-running form: there the one idle trace per pixel is not small against the pixel's work.
+// ---------------------------------------------------------------------------
+// closest-hit half: what follows the trace of this slot's closest-hit (or primary) ray
+__device__ __forceinline__ void ls_closest(const RenderParams& p, Slot& t, int closest, float tmin, uint32_t& rays, uint32_t& traced,
+                                           uint32_t& paths)
+{
+    if (!t.alive)
+        return;
+    bool restart = !t.ray; // the path ended in the shade half: start the next frame's path here
+    if (t.ray)
+    {
+        traced++;
+        if (t.fresh)
+        {
+            // the primary ray of a newly claimed pixel: its hit serves every frame (see slot_advance)
+            t.fresh = false;
+            t.tPrimary = tmin;
+            t.cPrimary = closest;
+            if (closest < 0)
+            {
+                accumulate_sky(p, t.acc, p.nFrames);
+                rays += p.nFrames;
+                t.j = p.nFrames;
+                slot_retire(p, t, paths);
+                t.ray = false;
+                return;
+            }
+            restart = true;
+        }
+        else
+        {
+            rays++;
+            if (closest < 0)
+            {
+                path_miss(p, t.s);
+                accumulate_sample(t.acc, t.s);
+                t.j++;
+                restart = true;
+            }
+        }
+    }
+    if (restart)
+    {
+        if (t.j >= p.nFrames)
+        {
+            slot_retire(p, t, paths);
+            t.ray = false;
+            return;
+        }
+        path_begin(t.s, p.cam.pos, t.d0, t.pixel, p.firstFrame + t.j * p.frameStride);
+        rays++; // the primary traceRay call this path starts with
+        closest = t.cPrimary;
+        tmin = t.tPrimary;
+    }
+    path_hit(p, t.s, __ldg(p.spheres + closest), closest, tmin);
+    t.ray = true; // a shadow ray is in flight (without lights: the bounce is pending)
+}
+
+// shade half: what follows the trace of this slot's shadow ray
+__device__ __forceinline__ void ls_shade(const RenderParams& p, Slot& t, int closest, float tmin, uint32_t& rays, uint32_t& traced,
+                                         uint32_t& paths)
+{
+    if (!t.alive || !t.ray)
+        return;
+    if (p.nLights > 0)
+    {
+        traced++;
+        rays++;
+        path_shadow(p, t.s, closest, tmin);
+    }
+    if (path_bounce(p, t.s))
+    {
+        accumulate_sample(t.acc, t.s);
+        t.j++;
+        t.ray = false; // restarts with the next closest-hit half
+        if (t.j >= p.nFrames)
+            slot_retire(p, t, paths); // the pixel is complete: the slot claims a new one before the next trace
+    }
+}
+
+template <bool kChunked>
+__global__ void __launch_bounds__(256, 2) megakernel_pair_ls(const RenderParams p)
+{
+    extern __shared__ float4 smem[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);        // kChunked: one mbarrier per staging buffer
+    uint32_t* candS = reinterpret_cast<uint32_t*>(smem + 1);   // candWords x blockDim.x candidate words
+    float4* sphS = smem + 1 + cand_words(p) * 256u / 4u;
+    constexpr unsigned kFull = 0xffffffffu;
+    uint32_t phase = 0u;
+
+    if (!kChunked)
+        stage_spheres(sphS, p.sphFilter, p.nSpheres);
+    else
+    {
+        const uint32_t words = 2u * round_up8(p.chunkSpheres);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+            sphS[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&mbar[0], 1u);
+            mbar_init(&mbar[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    Slot a, b;
+    a.alive = b.alive = false;
+    a.fresh = b.fresh = false;
+    a.shadow = b.shadow = false;
+    a.ray = b.ray = false;
+    a.j = b.j = 0;
+    a.frame = b.frame = 0;
+    a.pixel = b.pixel = 0;
+    a.tPrimary = b.tPrimary = 0.0f;
+    a.cPrimary = b.cPrimary = -1;
+    a.acc = b.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    a.d0 = b.d0 = { 0.0f, 0.0f, 0.0f };
+    path_begin(a.s, p.cam.pos, a.d0, 0u, 0u);
+    path_begin(b.s, p.cam.pos, b.d0, 0u, 0u);
+    bool exhausted = false;
+    uint32_t rays = 0, traced = 0, paths = 0;
+
+    while (true)
+    {
+        // ---- claim pixels for idle slots: their primary rays join the closest-hit trace below ----
+        const bool needA = !a.alive && !exhausted, needB = !b.alive && !exhausted;
+        const uint32_t nNeed = __popc(__ballot_sync(kFull, needA)) + __popc(__ballot_sync(kFull, needB));
+        const bool anyAlive = __any_sync(kFull, a.alive || b.alive);
+        if (nNeed != 0u && (nNeed >= 2u * p.claimThreshold || !anyAlive))
+        {
+            const uint32_t idA = pool_claim(p.pool, needA);
+            if (needA)
+                slot_claim(p, a, idA, exhausted, paths);
+            const uint32_t idB = pool_claim(p.pool, needB && !exhausted);
+            if (needB && !exhausted)
+                slot_claim(p, b, idB, exhausted, paths);
+        }
+        if (kChunked)
+        {
+            if (!__syncthreads_or(a.alive || b.alive || !exhausted))
+                break;
+        }
+        else if (!__any_sync(kFull, a.alive || b.alive))
+        {
+            if (__all_sync(kFull, exhausted))
+                break;
+            continue;
+        }
+
+        float tmin0, tmin1;
+        int closest0, closest1;
+        // ---- C: closest-hit rays of every slot (Renderer::traceRay), then path_hit for all of them ----
+        trace_pair<kChunked>(p, sphS, candS, mbar, phase, a, b, a.alive && a.ray, b.alive && b.ray, tmin0, closest0, tmin1, closest1);
+        ls_closest(p, a, closest0, tmin0, rays, traced, paths);
+        ls_closest(p, b, closest1, tmin1, rays, traced, paths);
+        // ---- S: shadow rays of every slot, then Cook-Torrance, roulette and the next direction for all of them ----
+        if (p.nLights > 0)
+            trace_pair<kChunked>(p, sphS, candS, mbar, phase, a, b, a.alive && a.ray, b.alive && b.ray, tmin0, closest0, tmin1, closest1);
+        ls_shade(p, a, closest0, tmin0, rays, traced, paths);
+        ls_shade(p, b, closest1, tmin1, rays, traced, paths);
     }
     count_rays(p, rays, traced, paths);
 }
@@ -1410,12 +1595,14 @@ cudaError_t pack_scene(const float* sphAoS, uint32_t nS, const float* matAoS, ui
 int mega_kind(const RenderParams& p, int requested)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
+    // the packed form runs in lockstep (megakernel_pair_ls) when a launch has enough frames per pixel
+    const int pairKind = p.nFrames >= kLockstepMinFrames ? kMegaPairLockstep : kMegaPair;
     if (chunked)
-        return kMegaPair;
-    if (requested == kMegaWhileWhile || requested == kMegaPair || requested == kMegaWarpQueue)
+        return (requested == kMegaPair || requested == kMegaPairLockstep) ? requested : pairKind;
+    if (requested == kMegaWhileWhile || requested == kMegaPair || requested == kMegaWarpQueue || requested == kMegaPairLockstep)
         return requested;
     if (p.nSpheres > kWhileWhileMaxSpheres)
-        return kMegaPair;
+        return pairKind;
     // The warp-queue form pays off where the first bounce is cached per pixel (at most one light) and a launch
     // has enough frames for the hit queue to fill. With several lights every frame starts with a full bounce, all
     // lanes need it at once, and the while-while form runs it without the trip through the queue (measured on 12
@@ -1448,6 +1635,12 @@ cudaError_t configure()
     if (e != cudaSuccess)
         return e;
     e = cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    e = cudaFuncSetAttribute(megakernel_pair_ls<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
+    e = cudaFuncSetAttribute(megakernel_pair_ls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
     e = cudaFuncSetAttribute(megakernel_wq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
@@ -1507,7 +1700,12 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
     else
     {
         const uint32_t grid = min(static_cast<uint32_t>(smCount) * 2u, (byWork + 1u) / 2u);
-        if (chunked)
+        const bool lockstep = mega_kind(p, kind) == kMegaPairLockstep;
+        if (chunked && lockstep)
+            megakernel_pair_ls<true><<<grid, 256, smem, s>>>(p);
+        else if (lockstep)
+            megakernel_pair_ls<false><<<grid, 256, smem, s>>>(p);
+        else if (chunked)
             megakernel_pair<true><<<grid, 256, smem, s>>>(p);
         else
             megakernel_pair<false><<<grid, 256, smem, s>>>(p);

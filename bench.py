@@ -272,7 +272,7 @@ def make_renderer(atx, name, local_rank, args=None):
     return r, cam, scene, spheres, mats, lights
 
 
-FORMS = {0: "wavefront", 1: "while-while", 2: "two-slot packed", 3: "warp-queue"}
+FORMS = {0: "wavefront", 1: "while-while", 2: "two-slot packed", 3: "warp-queue", 4: "two-slot packed, lockstep"}
 
 
 def secondary_workload(atx, name, local_rank, flush, steps=2, warmup=3):

@@ -147,7 +147,10 @@ enum {
                                    packed (two pixels per thread, f32x2 sphere loop), 3 = warp-queue
                                    (one 8x4 tile per warp, hits queued in shared memory and bounced 32
                                    at a time; the automatic choice for <= 16 spheres, at most one light
-                                   and >= 4 frames per launch) */
+                                   and >= 4 frames per launch), 4 = two-slot packed in lockstep (every
+                                   slot of a CTA alternates closest-hit and shadow traces together, so the
+                                   shading between traces runs warp-wide; the automatic choice above 16
+                                   spheres from 4 frames per launch) */
     ATX_TUNE_PARK_THRESHOLD = 3 /* while-while form: parked hits per warp (1..32) that trigger the
                                    bounce phase (default 8) */,
     ATX_TUNE_CLAIM_THRESHOLD = 4 /* idle lanes per warp (1..32) that trigger a batched claim from the
@@ -195,7 +198,7 @@ ATX_API atx_status atx_sync(atx_handle h);
  * call's kernels. Synchronises. */
 ATX_API atx_status atx_last_render_ms(atx_handle h, float* out_ms);
 
-/* Megakernel form the last launch used (1 while-while, 2 two-slot packed, 3 warp-queue; 0 before any launch
+/* Megakernel form the last launch used (1 while-while, 2 two-slot packed, 3 warp-queue, 4 two-slot packed in lockstep; 0 before any launch
  * or after a wavefront launch): what ATX_TUNE_MEGA_KIND = 0 resolved to. */
 ATX_API atx_status atx_last_mega_kind(atx_handle h, int* out);
 

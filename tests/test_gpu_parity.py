@@ -186,14 +186,15 @@ def test_live_synthetic_scenes(atx, tmp_path):
         _live_compare(atx, p, 320, 180, 8, i == 0, 3)
 
 
-@pytest.mark.parametrize("name,frames", [("config3", 33), ("config4", 4)])
+@pytest.mark.parametrize("name,frames", [("config3", 33), ("config4", 6)])
 def test_config3_config4_full_resolution_vs_live_reference(atx, tmp_path, name, frames):
     """BASELINE configs 3 and 4 at their full 3840x2160 (256 spheres / 16 lights; 4096 spheres), a few frames of
-    the reference (its brute-force kernel needs ~0.1-1 s per 4K frame): two-slot packed form, bit for bit."""
+    the reference (its brute-force kernel needs 15-190 ms per 4K frame): frame 1 with the free-running two-slot packed
+    form, the remaining frames in one launch of the lockstep form, bit for bit."""
     scene = getattr(atx.synthetic, name)()
     p = tmp_path / f"{name}.json"
     atx.Utils.exportScene(scene, str(p))
-    _live_compare(atx, p, 3840, 2160, 8, False, frames)
+    _live_compare(atx, p, 3840, 2160, 8, False, frames, expect_kind=atx.MEGA_PAIR_LOCKSTEP)
 
 
 def test_live_small_scene_several_lights_every_form(atx, tmp_path):
@@ -210,6 +211,8 @@ def test_live_small_scene_several_lights_every_form(atx, tmp_path):
     _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE)
     _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE, one_launch=True)
     _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_PAIR, expect_kind=atx.MEGA_PAIR)
+    _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP)
+    _live_compare(atx, p, 240, 136, 8, True, 24, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
     scene2 = atx.synthetic.small(5, 2, seed=3)
     p2 = tmp_path / "cs2.json"
     atx.Utils.exportScene(scene2, str(p2))
@@ -226,6 +229,8 @@ def test_live_natural_chunked_staging(atx, tmp_path):
     atx.Utils.exportScene(scene, str(p))
     _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR)
     _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR, one_launch=True)
+    _live_compare(atx, p, 192, 108, 8, False, 6, expect_kind=atx.MEGA_PAIR_LOCKSTEP)                   # 1 + 5 frames: lockstep, chunked
+    _live_compare(atx, p, 192, 108, 8, False, 6, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
 
 
 def test_live_wavefront_variant(atx, tmp_path):
@@ -313,11 +318,14 @@ def test_chunked_staging_is_bit_identical(atx):
     r, cam = setup(atx, scene, 192, 108, 6, True)
     r.Render(cam, scene, frames=3)
     base = r.getAccumulation()
-    for chunk in (1, 7, 8, 16, 32, 39, 40):
-        r.setTuning(atx.TUNE_CHUNK_SPHERES, chunk)
-        r.resetFrameIndex()
-        r.Render(cam, scene, frames=3)
-        assert (bits(r.getAccumulation()) == bits(base)).all(), chunk
+    for kind in (atx.MEGA_PAIR, atx.MEGA_PAIR_LOCKSTEP):
+        r.setTuning(atx.TUNE_MEGA_KIND, kind)
+        for chunk in (1, 7, 8, 16, 32, 39, 40):
+            r.setTuning(atx.TUNE_CHUNK_SPHERES, chunk)
+            r.resetFrameIndex()
+            r.Render(cam, scene, frames=3)
+            assert r.lastMegaKind() == kind
+            assert (bits(r.getAccumulation()) == bits(base)).all(), (kind, chunk)
     r.close()
 
 
@@ -332,7 +340,8 @@ def test_megakernel_forms_are_bit_identical(atx):
     for scene, W, H, bounces, sky, frames in cases:
         r, cam = setup(atx, scene, W, H, bounces, sky)
         ref = None
-        for kind, rounds in ((atx.MEGA_WHILE_WHILE, 1), (atx.MEGA_WHILE_WHILE, 12), (atx.MEGA_WHILE_WHILE, 32), (atx.MEGA_PAIR, 12)):
+        for kind, rounds in ((atx.MEGA_WHILE_WHILE, 1), (atx.MEGA_WHILE_WHILE, 12), (atx.MEGA_WHILE_WHILE, 32), (atx.MEGA_PAIR, 12),
+                             (atx.MEGA_PAIR_LOCKSTEP, 12)):
             r.setTuning(atx.TUNE_MEGA_KIND, kind)
             r.setTuning(atx.TUNE_PARK_THRESHOLD, rounds)
             r.resetFrameIndex(); r.resetCounters()
