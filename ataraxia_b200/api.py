@@ -507,6 +507,21 @@ class Renderer:
         a = np.ascontiguousarray(acc, np.float32)
         check(_capi.lib().atx_write_accum(self._h, vptr(a), next_frame_index))
 
+    def saveCheckpoint(self, path: str, next_frame_index: int = 0, frame_stride: int = 0) -> None:
+        """Accumulation buffer + next frame index on disk, bound to the scene and camera by a hash (atx_save_checkpoint)."""
+        check(_capi.lib().atx_save_checkpoint(self._h, str(path).encode(), int(next_frame_index), int(frame_stride)))
+
+    def loadCheckpoint(self, path: str):
+        """Resume: (next_frame_index, frame_stride). Refuses a file rendered with another size, scene, camera or settings."""
+        a, b = C.c_uint32(), C.c_uint32()
+        check(_capi.lib().atx_load_checkpoint(self._h, str(path).encode(), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sceneSha256(self) -> bytes:
+        buf = (C.c_uint8 * 32)()
+        check(_capi.lib().atx_scene_sha256(self._h, buf))
+        return bytes(buf)
+
     def getRGBA8(self, divisor: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.empty((self.m_height, self.m_width), np.uint32)

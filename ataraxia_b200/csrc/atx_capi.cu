@@ -145,6 +145,7 @@ struct atx_renderer
     int32_t* dSphMat = nullptr;
     size_t capS = 0, capM = 0, capL = 0;
     uint32_t nS = 0, nM = 0, nL = 0;
+    std::vector<uint8_t> hostScene; // the records as uploaded (spheres, materials, lights): what a checkpoint's scene hash covers
 
     CameraState cam;
     bool accumulation = true, skyLight = false;
@@ -375,6 +376,21 @@ atx_status atx_upload_scene(atx_handle h, const atx_sphere* spheres, size_t n_sp
     h->nS = static_cast<uint32_t>(n_spheres);
     h->nM = static_cast<uint32_t>(n_materials);
     h->nL = static_cast<uint32_t>(n_lights);
+    try
+    {
+        h->hostScene.clear();
+        const auto append = [&](const void* ptr, size_t bytes) {
+            const uint8_t* b = static_cast<const uint8_t*>(ptr);
+            h->hostScene.insert(h->hostScene.end(), b, b + bytes);
+        };
+        append(spheres, n_spheres * sizeof(atx_sphere));
+        append(materials, n_materials * sizeof(atx_material));
+        append(lights, n_lights * sizeof(atx_light));
+    }
+    catch (const std::bad_alloc&)
+    {
+        return fail(ATX_ERR_ALLOC, "out of host memory");
+    }
     ATX_CUDA(atx_launch::pack_scene(h->dSphAoS, h->nS, h->dMatAoS, h->nM, h->dLightAoS, h->nL, h->dSpheres, h->dSphFilter, h->dSphMat,
                                     h->dMats, h->dLights, h->stream));
     h->launches++;
@@ -842,6 +858,276 @@ atx_status atx_stream(atx_handle h, void** out_cuda_stream)
     *out_cuda_stream = h->stream;
     return ATX_OK;
 }
+
+} // extern "C"
+
+// ---- resumable renders on disk ---------------------------------
+// The accumulation buffer plus the next frame index is the complete state of a progressive render: the RNG is a
+// pure function of (pixel, frameIndex) (Renderer.cu:300-306) and the image is accumulation / frameIndex
+// (Renderer.cu:165-168, :181-182, :245-248). A checkpoint is that state, bound to the scene and camera it was
+// rendered with by a SHA-256 over the uploaded records and the camera matrices.
+namespace
+{
+struct Sha256
+{
+    uint32_t h[8] = { 0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u };
+    uint8_t block[64];
+    size_t fill = 0;
+    uint64_t total = 0;
+
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+    void compress(const uint8_t* b)
+    {
+        static const uint32_t K[64] = {
+            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, 0xd807aa98u, 0x12835b01u,
+            0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu,
+            0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u,
+            0x06ca6351u, 0x14292967u, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+            0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, 0x19a4c116u, 0x1e376c08u,
+            0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u,
+            0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u };
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++)
+            w[i] = (uint32_t(b[4 * i]) << 24) | (uint32_t(b[4 * i + 1]) << 16) | (uint32_t(b[4 * i + 2]) << 8) | uint32_t(b[4 * i + 3]);
+        for (int i = 16; i < 64; i++)
+        {
+            const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t v[8];
+        std::memcpy(v, h, sizeof(v));
+        for (int i = 0; i < 64; i++)
+        {
+            const uint32_t S1 = rotr(v[4], 6) ^ rotr(v[4], 11) ^ rotr(v[4], 25);
+            const uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+            const uint32_t t1 = v[7] + S1 + ch + K[i] + w[i];
+            const uint32_t S0 = rotr(v[0], 2) ^ rotr(v[0], 13) ^ rotr(v[0], 22);
+            const uint32_t maj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+            const uint32_t t2 = S0 + maj;
+            v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1;
+            v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
+        }
+        for (int i = 0; i < 8; i++)
+            h[i] += v[i];
+    }
+
+    void update(const void* data, size_t n)
+    {
+        const uint8_t* p = static_cast<const uint8_t*>(data);
+        total += n;
+        while (n)
+        {
+            const size_t take = std::min(n, sizeof(block) - fill);
+            std::memcpy(block + fill, p, take);
+            fill += take; p += take; n -= take;
+            if (fill == sizeof(block))
+            {
+                compress(block);
+                fill = 0;
+            }
+        }
+    }
+
+    void finish(uint8_t out[32])
+    {
+        const uint64_t bits = total * 8u;
+        const uint8_t one = 0x80, zero = 0;
+        update(&one, 1);
+        while (fill != 56)
+            update(&zero, 1);
+        uint8_t len[8];
+        for (int i = 0; i < 8; i++)
+            len[i] = static_cast<uint8_t>(bits >> (56 - 8 * i));
+        update(len, 8);
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 4; j++)
+                out[4 * i + j] = static_cast<uint8_t>(h[i] >> (24 - 8 * j));
+    }
+};
+
+struct CheckpointHeader // 160 bytes, little-endian, no padding
+{
+    char magic[8];          // "ATXCKPT1"
+    uint32_t version;       // 1
+    uint32_t headerBytes;   // sizeof(CheckpointHeader)
+    uint32_t width, height;
+    uint32_t nextFrameIndex; // the frame index the render continues with
+    uint32_t frameStride;    // 1, or the number of ranks of an spp-split render (this file is one rank's share)
+    int32_t accumulation, skyLight, maxBounces;
+    uint32_t nSpheres, nMaterials, nLights;
+    int32_t rank, nRanks;    // communicator coordinates at save time (0, 1 without a communicator)
+    uint64_t payloadBytes;   // width * height * 16
+    uint8_t sceneSha256[32]; // uploaded scene records + camera position + inverse projection + inverse view
+    uint8_t payloadSha256[32];
+    uint8_t reserved[24];
+};
+static_assert(sizeof(CheckpointHeader) == 160, "checkpoint header layout");
+
+void scene_digest(atx_handle h, uint8_t out[32])
+{
+    Sha256 sha;
+    const uint32_t counts[3] = { h->nS, h->nM, h->nL };
+    sha.update(counts, sizeof(counts));
+    if (!h->hostScene.empty())
+        sha.update(h->hostScene.data(), h->hostScene.size());
+    sha.update(h->cam.pos, sizeof(h->cam.pos));
+    sha.update(&h->cam.invProj, 64);
+    sha.update(&h->cam.invView, 64);
+    sha.finish(out);
+}
+} // namespace
+
+extern "C" {
+
+atx_status atx_host_sha256(const void* data, size_t bytes, uint8_t out[32])
+{
+    if ((!data && bytes) || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    Sha256 sha;
+    sha.update(data, bytes);
+    sha.finish(out);
+    return ATX_OK;
+}
+
+atx_status atx_scene_sha256(atx_handle h, uint8_t out[32])
+{
+    if (!h || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    if (!h->cam.set)
+        return fail(ATX_ERR_INVALID, "no camera: the scene hash covers the camera matrices");
+    scene_digest(h, out);
+    return ATX_OK;
+}
+
+atx_status atx_save_checkpoint(atx_handle h, const char* path, uint32_t next_frame_index, uint32_t frame_stride)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!path)
+        return fail(ATX_ERR_INVALID, "path is null");
+    if (!h->dAccum || !h->cam.set)
+        return fail(ATX_ERR_INVALID, "nothing to save: atx_resize and a camera come first");
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    std::vector<float> acc;
+    try
+    {
+        acc.resize(P * 4);
+    }
+    catch (const std::bad_alloc&)
+    {
+        return fail(ATX_ERR_ALLOC, "out of host memory");
+    }
+    ATX_CUDA(cudaMemcpyAsync(acc.data(), h->dAccum, P * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    CheckpointHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    std::memcpy(hd.magic, "ATXCKPT1", 8);
+    hd.version = 1;
+    hd.headerBytes = sizeof(hd);
+    hd.width = h->width;
+    hd.height = h->height;
+    hd.nextFrameIndex = next_frame_index ? next_frame_index : h->frameIndex;
+    hd.frameStride = frame_stride ? frame_stride : 1u;
+    hd.accumulation = h->accumulation;
+    hd.skyLight = h->skyLight;
+    hd.maxBounces = h->maxBounces;
+    hd.nSpheres = h->nS; hd.nMaterials = h->nM; hd.nLights = h->nL;
+    hd.rank = h->rank; hd.nRanks = h->nRanks;
+    hd.payloadBytes = P * sizeof(float4);
+    scene_digest(h, hd.sceneSha256);
+    Sha256 sha;
+    sha.update(acc.data(), hd.payloadBytes);
+    sha.finish(hd.payloadSha256);
+    // write to a temporary name and rename: a crash mid-write never leaves a half checkpoint under `path`
+    const std::string tmp = std::string(path) + ".part";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f)
+        return fail(ATX_ERR_INVALID, "cannot open %s for writing", tmp.c_str());
+    const bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1 && std::fwrite(acc.data(), 1, hd.payloadBytes, f) == hd.payloadBytes;
+    const bool closed = std::fclose(f) == 0;
+    if (!ok || !closed || std::rename(tmp.c_str(), path) != 0)
+    {
+        std::remove(tmp.c_str());
+        return fail(ATX_ERR_INVALID, "writing %s failed", path);
+    }
+    return ATX_OK;
+}
+
+atx_status atx_load_checkpoint(atx_handle h, const char* path, uint32_t* next_frame_index, uint32_t* frame_stride)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!path)
+        return fail(ATX_ERR_INVALID, "path is null");
+    if (!h->dAccum || !h->cam.set)
+        return fail(ATX_ERR_INVALID, "atx_resize, the scene and the camera come before atx_load_checkpoint (the file is checked against them)");
+    FILE* f = std::fopen(path, "rb");
+    if (!f)
+        return fail(ATX_ERR_INVALID, "cannot open %s", path);
+    CheckpointHeader hd;
+    atx_status st = ATX_OK;
+    std::vector<float> acc;
+    if (std::fread(&hd, sizeof(hd), 1, f) != 1 || std::memcmp(hd.magic, "ATXCKPT1", 8) != 0)
+        st = fail(ATX_ERR_INVALID, "%s is not a checkpoint of this library", path);
+    else if (hd.version != 1 || hd.headerBytes != sizeof(hd))
+        st = fail(ATX_ERR_INVALID, "%s: unsupported checkpoint version %u", path, hd.version);
+    else if (hd.width != h->width || hd.height != h->height)
+        st = fail(ATX_ERR_INVALID, "%s holds a %ux%u image, the renderer is %ux%u", path, hd.width, hd.height, h->width, h->height);
+    else if (hd.payloadBytes != static_cast<uint64_t>(h->width) * h->height * sizeof(float4) || hd.nextFrameIndex == 0 || hd.frameStride == 0)
+        st = fail(ATX_ERR_INVALID, "%s: inconsistent header", path);
+    else if (hd.maxBounces != h->maxBounces || (hd.skyLight != 0) != h->skyLight)
+        st = fail(ATX_ERR_INVALID, "%s was rendered with maxBounces %d / skyLight %d, the renderer is set to %d / %d", path, hd.maxBounces,
+                  hd.skyLight, h->maxBounces, int(h->skyLight));
+    else
+    {
+        uint8_t now[32];
+        scene_digest(h, now);
+        if (std::memcmp(now, hd.sceneSha256, 32) != 0)
+            st = fail(ATX_ERR_INVALID, "%s was rendered with a different scene or camera (scene hash mismatch): continuing it would mix two images", path);
+    }
+    if (st == ATX_OK)
+    {
+        try
+        {
+            acc.resize(hd.payloadBytes / sizeof(float));
+        }
+        catch (const std::bad_alloc&)
+        {
+            st = fail(ATX_ERR_ALLOC, "out of host memory");
+        }
+    }
+    if (st == ATX_OK)
+    {
+        uint8_t extra;
+        if (std::fread(acc.data(), 1, hd.payloadBytes, f) != hd.payloadBytes || std::fread(&extra, 1, 1, f) != 0)
+            st = fail(ATX_ERR_INVALID, "%s is truncated or has trailing bytes", path);
+        else
+        {
+            uint8_t digest[32];
+            Sha256 sha;
+            sha.update(acc.data(), hd.payloadBytes);
+            sha.finish(digest);
+            if (std::memcmp(digest, hd.payloadSha256, 32) != 0)
+                st = fail(ATX_ERR_INVALID, "%s: payload checksum mismatch (corrupt file)", path);
+        }
+    }
+    std::fclose(f);
+    if (st != ATX_OK)
+        return st;
+    ATX_CUDA(cudaMemcpyAsync(h->dAccum, acc.data(), hd.payloadBytes, cudaMemcpyHostToDevice, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    h->frameIndex = hd.nextFrameIndex;
+    h->lastFrame = hd.nextFrameIndex > 1 ? hd.nextFrameIndex - 1 : 1;
+    if (next_frame_index) *next_frame_index = hd.nextFrameIndex;
+    if (frame_stride) *frame_stride = hd.frameStride;
+    return ATX_OK;
+}
+
+} // extern "C"
+
+extern "C" {
 
 // ---- multi-GPU ---------------------------------------------------------------
 

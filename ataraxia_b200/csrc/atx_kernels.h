@@ -23,6 +23,7 @@ constexpr int kMegaPair = 2;       // two pixels per thread, packed f32x2 sphere
 constexpr int kMegaWarpQueue = 3;  // one tile per warp, hits queued in shared memory and bounced 32 at a time
 constexpr int kMegaPairLockstep = 4; // two-slot packed form, every slot of the CTA alternates closest-hit and shadow traces together
 constexpr uint32_t kLockstepMinFrames = 4; // frames per launch from which the packed form runs in lockstep
+constexpr uint32_t kLockstepMaxSpheres = 1536; // ... up to this many spheres (beyond, the free-running form wins)
 constexpr uint32_t kWhileWhileMaxSpheres = 16;
 constexpr uint32_t kWarpQueueMinFrames = 4;  // frames per launch from which the warp-queue form replaces the while-while form
                                              // (config 2 geometry, ms per launch, while-while / warp-queue: 1 frame 0.128 / 0.156,

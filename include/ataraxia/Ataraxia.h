@@ -512,6 +512,16 @@ public:
         return hits;
     }
     atx_counters counters() const { atx_counters c{}; atx_get_counters(m_handle, &c); return c; }
+    // resumable render on disk: accumulation + next frame index, bound to scene and camera by a hash.
+    // loadCheckpoint refuses (false + message) a file rendered with another size, scene, camera or settings.
+    bool saveCheckpoint(const std::string& path) const
+    {
+        return atx_save_checkpoint(m_handle, path.c_str(), 0, 0) == ATX_OK || (report("saveCheckpoint"), false);
+    }
+    bool loadCheckpoint(const std::string& path)
+    {
+        return atx_load_checkpoint(m_handle, path.c_str(), nullptr, nullptr) == ATX_OK || (report("loadCheckpoint"), false);
+    }
     // float radiance (accumulation / samples, unclamped) as a little-endian PFM, bottom row first as PFM defines it
     bool saveAccumulationPFM(const std::string& path) const
     {

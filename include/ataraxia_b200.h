@@ -217,6 +217,29 @@ ATX_API atx_status atx_read_accum(atx_handle h, float* dst);
  * resumable-render state. */
 ATX_API atx_status atx_write_accum(atx_handle h, const float* src, uint32_t next_frame_index);
 
+/* ---- resumable renders on disk ---------------------------- */
+
+/* The complete state of a progressive render is the accumulation buffer and the next frame index
+ * (Renderer.cu:165-168, :181-182, :245-248: the RNG is a pure function of pixel and frameIndex).
+ * atx_save_checkpoint writes both to `path` (160-byte header + width*height float4), bound to the scene and
+ * camera by a SHA-256 over the uploaded records and the camera matrices, with a SHA-256 of the payload.
+ * next_frame_index = 0 means "the handle's frameIndex" (what atx_render continues with); callers that drive
+ * atx_render_frames themselves (one rank's share of an spp-split render) pass their own next frame index and
+ * frame_stride (0 = 1). Written to `path`.part and renamed. */
+ATX_API atx_status atx_save_checkpoint(atx_handle h, const char* path, uint32_t next_frame_index, uint32_t frame_stride);
+
+/* Load a checkpoint into the accumulation buffer and set frameIndex. The renderer must already have the
+ * image size, scene, camera and settings the file was rendered with: a different size, maxBounces, skyLight,
+ * or scene/camera hash is refused with ATX_ERR_INVALID (continuing would mix two images), as is a truncated or
+ * corrupt file. Continuing after a load is bit-identical to never having stopped. */
+ATX_API atx_status atx_load_checkpoint(atx_handle h, const char* path, uint32_t* next_frame_index, uint32_t* frame_stride);
+
+/* SHA-256 of what a checkpoint binds to: uploaded scene records, camera position and the two inverse matrices. */
+ATX_API atx_status atx_scene_sha256(atx_handle h, uint8_t out[32]);
+
+/* SHA-256 of a host buffer (the digest used above; exposed so callers can verify read-backs). */
+ATX_API atx_status atx_host_sha256(const void* data, size_t bytes, uint8_t out[32]);
+
 /* RGBA8 image as Renderer::Render leaves it in h_imageData_ (Renderer.cu:165-168,
  * :240; packing colorUtils::vec4ToRGBA, Renderer.h:70-78): clamp(acc/divisor,0,1),
  * truncating, alpha from acc.w. divisor = 0 means "frameIndex of the last

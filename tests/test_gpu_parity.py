@@ -19,7 +19,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -194,7 +194,9 @@ def test_config3_config4_full_resolution_vs_live_reference(atx, tmp_path, name, 
     scene = getattr(atx.synthetic, name)()
     p = tmp_path / f"{name}.json"
     atx.Utils.exportScene(scene, str(p))
-    _live_compare(atx, p, 3840, 2160, 8, False, frames, expect_kind=atx.MEGA_PAIR_LOCKSTEP)
+    _live_compare(atx, p, 3840, 2160, 8, False, frames, expect_kind=atx.MEGA_PAIR_LOCKSTEP if name == "config3" else atx.MEGA_PAIR)
+    if name == "config4":
+        _live_compare(atx, p, 3840, 2160, 8, False, frames, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP)
 
 
 def test_live_small_scene_several_lights_every_form(atx, tmp_path):
@@ -229,8 +231,8 @@ def test_live_natural_chunked_staging(atx, tmp_path):
     atx.Utils.exportScene(scene, str(p))
     _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR)
     _live_compare(atx, p, 192, 108, 8, False, 3, expect_kind=atx.MEGA_PAIR, one_launch=True)
-    _live_compare(atx, p, 192, 108, 8, False, 6, expect_kind=atx.MEGA_PAIR_LOCKSTEP)                   # 1 + 5 frames: lockstep, chunked
-    _live_compare(atx, p, 192, 108, 8, False, 6, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
+    _live_compare(atx, p, 192, 108, 8, False, 6, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP)   # lockstep, chunked
+    _live_compare(atx, p, 192, 108, 8, False, 6, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
 
 
 def test_live_wavefront_variant(atx, tmp_path):
@@ -527,6 +529,83 @@ def test_settings_and_edge_cases(atx, port):
     r2.setAccumulation(saved, 3)
     r2.Render(cam2, scene)
     assert (bits(r2.getAccumulation()) == bits(full)).all()
+    r.close(); r2.close()
+
+
+def test_checkpoint_on_disk_resumes_bit_identically(atx, tmp_path):
+    """(accumulation, frameIndex, scene hash) on disk. Render 1..k, save, a NEW PROCESS loads and renders
+    k+1..n: identical to the uninterrupted render, bit for bit. A file rendered with another scene, camera, size or
+    settings, a truncated file and a corrupted payload are all refused; a refused load leaves the renderer untouched."""
+    import subprocess
+    import sys
+    scene_path = GOLDEN / "small_scene.json"
+    scene = atx.Utils.importScene(str(scene_path))
+    W, H, bounces, k, n = 160, 90, 6, 5, 12
+    r, cam = setup(atx, scene, W, H, bounces, True)
+    r.Render(cam, scene, frames=n)
+    full = r.getAccumulation()
+    r.resetFrameIndex()
+    r.Render(cam, scene, frames=k)
+    ck = tmp_path / "render.atxckpt"
+    r.saveCheckpoint(ck)
+    assert not (tmp_path / "render.atxckpt.part").exists() and ck.stat().st_size == 160 + W * H * 16
+    out = tmp_path / "resumed.npy"
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {str(ROOT)!r})
+import ataraxia_b200 as atx
+scene = atx.Utils.importScene({str(scene_path)!r})
+cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+r = atx.Renderer(0); r.setSettings(atx.Settings(True, True, {bounces})); r.onResize({W}, {H}); cam.Resize({W}, {H})
+r.uploadScene(scene); r.m_scene = scene; r.setCamera(cam)
+nxt, stride = r.loadCheckpoint({str(ck)!r})
+assert (nxt, stride) == ({k + 1}, 1) and r.frameIndex() == {k + 1}
+r.Render(cam, scene, frames={n - k})
+np.save({str(out)!r}, r.getAccumulation())
+"""
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert (bits(np.load(out)) == bits(full)).all()
+    # refusals
+    before, fi = r.getAccumulation(), r.frameIndex()
+    data = ck.read_bytes()
+    (tmp_path / "short.ckpt").write_bytes(data[:-7])
+    bad = bytearray(data); bad[160 + 1000] ^= 0x40
+    (tmp_path / "flipped.ckpt").write_bytes(bytes(bad))
+    (tmp_path / "junk.ckpt").write_bytes(b"not a checkpoint" * 20)
+    for name in ("short.ckpt", "flipped.ckpt", "junk.ckpt", "missing.ckpt"):
+        with pytest.raises(atx.AtxError):
+            r.loadCheckpoint(tmp_path / name)
+    r.setSettings(atx.Settings(True, True, bounces + 1))
+    with pytest.raises(atx.AtxError, match="maxBounces"):
+        r.loadCheckpoint(ck)
+    r.setSettings(atx.Settings(True, True, bounces))
+    cam2 = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition() + np.float32([0.25, 0.0, 0.0]), scene.camera.getDirection())
+    cam2.Resize(W, H)
+    r.setCamera(cam2)
+    with pytest.raises(atx.AtxError, match="scene hash"):
+        r.loadCheckpoint(ck)                                        # same scene, camera moved
+    r.setCamera(cam)
+    other = atx.synthetic.small(12, 2, seed=4)
+    r.uploadScene(other)
+    with pytest.raises(atx.AtxError, match="scene hash"):
+        r.loadCheckpoint(ck)                                        # another scene
+    r.uploadScene(scene)
+    assert (bits(r.getAccumulation()) == bits(before)).all() and r.frameIndex() == fi
+    assert r.loadCheckpoint(ck) == (k + 1, 1)                      # and the right one still loads
+    r2, cam3 = setup(atx, scene, W + 8, H, bounces, True)
+    r2.uploadScene(scene); r2.setCamera(cam3)
+    with pytest.raises(atx.AtxError, match="image"):
+        r2.loadCheckpoint(ck)                                       # another size
+    # one rank's share of an spp-split render: caller-supplied next frame and stride travel with the file
+    r.renderFrames(2, 3, 4, zero_first=True)                        # frames 2, 6, 10 of a 4-rank split
+    share_ck = tmp_path / "rank1.ckpt"
+    r.saveCheckpoint(share_ck, next_frame_index=14, frame_stride=4)
+    r.renderFrames(14, 2, 4, zero_first=False)
+    want = r.getAccumulation()
+    assert r.loadCheckpoint(share_ck) == (14, 4)
+    r.renderFrames(14, 2, 4, zero_first=False)
+    assert (bits(r.getAccumulation()) == bits(want)).all()
     r.close(); r2.close()
 
 

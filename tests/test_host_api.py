@@ -328,3 +328,20 @@ def test_frame_partition():
             assert max(counts) - min(counts) <= 1
     with pytest.raises(ValueError):
         frame_partition(4, 2, 2)
+
+
+def test_sha256_matches_hashlib(built):
+    """atx_host_sha256 (the digest checkpoints bind scene and payload with) against hashlib on block-boundary sizes."""
+    import ctypes as C
+    import hashlib
+    from ataraxia_b200 import _capi
+    lib = _capi.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 1000, 65536 + 3):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        out = (C.c_uint8 * 32)()
+        assert lib.atx_host_sha256(data, n, out) == _capi.ATX_OK
+        assert bytes(out) == hashlib.sha256(data).digest(), n
+    assert lib.atx_host_sha256(None, 4, (C.c_uint8 * 32)()) == _capi.ATX_ERR_INVALID
+    assert lib.atx_save_checkpoint(None, b"x", 0, 0) == _capi.ATX_ERR_INVALID
+    assert lib.atx_load_checkpoint(None, b"x", None, None) == _capi.ATX_ERR_INVALID
