@@ -8,7 +8,7 @@ from .api import (Ataraxia, Camera, Image, InputState, Light, Material, Renderer
                   pack_lights, pack_materials, pack_spheres, traverseSceneGraph)
 from . import utils as Utils  # noqa: F401  (namespace Utils, Engine/include/Utils.h)
 from . import synthetic  # noqa: F401
-from ._capi import (AtxError, LIGHT_DTYPE, MATERIAL_DTYPE, SPHERE_DTYPE, TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD,  # noqa: F401
+from ._capi import (AtxError, LIGHT_DTYPE, MATERIAL_DTYPE, SPHERE_DTYPE, TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD, TUNE_REDUCE, REDUCE_NONE, REDUCE_PEER_MEMORY, REDUCE_NCCL,  # noqa: F401
                     MEGA_AUTO, MEGA_PAIR, MEGA_PAIR_LOCKSTEP, MEGA_WHILE_WHILE, MEGA_WARP_QUEUE,
                     VARIANT_AUTO, VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT)
 

@@ -26,13 +26,14 @@ SYMBOLS = [
     "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum", "atx_allreduce_preview", "atx_read_preview",
     "atx_host_camera_matrices", "atx_host_ray_directions", "atx_host_node_transform", "atx_host_transform_sphere", "atx_host_mat4_mul",
     "atx_host_camera_update",
-    "atx_save_checkpoint", "atx_load_checkpoint", "atx_scene_sha256", "atx_host_sha256",
+    "atx_save_checkpoint", "atx_load_checkpoint", "atx_scene_sha256", "atx_host_sha256", "atx_last_reduce_kind",
 ]
 
 ATX_OK = 0
 ATX_ERR_INVALID, ATX_ERR_CUDA, ATX_ERR_NCCL, ATX_ERR_NO_DEVICE, ATX_ERR_ALLOC = -1, -2, -3, -4, -5
 VARIANT_AUTO, VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1, 2
-TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD = 1, 2, 3, 4
+TUNE_CHUNK_SPHERES, TUNE_MEGA_KIND, TUNE_PARK_THRESHOLD, TUNE_CLAIM_THRESHOLD, TUNE_REDUCE = 1, 2, 3, 4, 5
+REDUCE_NONE, REDUCE_PEER_MEMORY, REDUCE_NCCL = 0, 1, 2
 MEGA_AUTO, MEGA_WHILE_WHILE, MEGA_PAIR, MEGA_WARP_QUEUE, MEGA_PAIR_LOCKSTEP = 0, 1, 2, 3, 4
 
 # numpy views of the reference PODs (SceneNode.h:11-21, Scene.h:17-47)
@@ -125,6 +126,7 @@ def lib() -> C.CDLL:
         "atx_load_checkpoint": [vp, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
         "atx_scene_sha256": [vp, C.POINTER(C.c_uint8)],
         "atx_host_sha256": [vp, C.c_size_t, C.POINTER(C.c_uint8)],
+        "atx_last_reduce_kind": [vp, C.POINTER(C.c_int)],
     }
     for name, argtypes in sig.items():
         fn = getattr(l, name)

@@ -575,6 +575,12 @@ class Renderer:
         return acc, rgba
     def allreduceAccum(self): check(_capi.lib().atx_allreduce_accum(self._h))
 
+    def lastReduceKind(self) -> int:
+        """Transport of the last allreduceAccum: REDUCE_PEER_MEMORY (one kernel over NVLink peer memory) or REDUCE_NCCL."""
+        v = C.c_int()
+        check(_capi.lib().atx_last_reduce_kind(self._h, C.byref(v)))
+        return v.value
+
 
 class Ataraxia:
     """Headless mirror of the `Ataraxia` layer (Engine/src/main.cpp:8-283): what the application does AROUND

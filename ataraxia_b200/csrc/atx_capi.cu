@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -56,6 +57,7 @@ struct NcclApi
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
     std::string loadError;
@@ -82,8 +84,9 @@ void load_nccl(NcclApi& api)
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.lib, "ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
     if (!api.ok)
         api.loadError = "symbols missing";
 }
@@ -162,10 +165,27 @@ struct atx_renderer
 
     ncclComm_t comm = nullptr;
     int nRanks = 1, rank = 0;
+
+    // peer-memory sum of the accumulation buffers (atx_p2p.cu): every rank's buffer and flag block mapped here by CUDA IPC
+    int reduceMode = 0;           // tuning: 0 = peer memory when it can be set up, 1 = ncclAllReduce
+    bool p2pReady = false;        // the tables below describe the current dAccum of every rank
+    bool p2pFailed = false;       // set-up was tried for this communicator and is not possible: NCCL from now on
+    bool p2pExported = false;     // peers may hold a mapping of dAccum: it must outlive them (see atx_resize)
+    float4* peerAccum[atx_launch::kP2pMaxRanks] = {};
+    uint32_t* peerFlags[atx_launch::kP2pMaxRanks] = {};
+    uint32_t* dP2pFlags = nullptr;
+    uint8_t* dP2pStage = nullptr; // IPC handles on their way through ncclAllGather, and the agreement word
+    uint32_t* hP2pError = nullptr; // mapped host memory
+    uint32_t p2pEpoch = 0;
+    int lastReduce = 0;           // 0 none yet, 1 peer memory, 2 NCCL
+    std::vector<void*> retired;   // accumulation buffers replaced by atx_resize while peers could still have them mapped
 };
 
 namespace
 {
+void p2p_teardown(atx_handle h, bool freeRetired); // peer-memory reduce: defined with the multi-GPU entry points
+atx_status p2p_check(atx_handle h);
+
 atx_status make_params(atx_handle h, atxk::RenderParams& p)
 {
     if (h->width == 0 || h->height == 0)
@@ -285,8 +305,12 @@ atx_status atx_destroy(atx_handle h)
         return ATX_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    p2p_teardown(h, true);
     if (h->comm && nccl().ok)
         nccl().CommDestroy(h->comm);
+    cudaFree(h->dP2pFlags); cudaFree(h->dP2pStage);
+    if (h->hP2pError)
+        cudaFreeHost(h->hP2pError);
     cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dSphFilter); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
@@ -326,7 +350,12 @@ atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height)
         return fail(ATX_ERR_ALLOC, "atx_resize(%u, %u): %s; the %ux%u image is kept", width, height, cudaGetErrorString(e),
                     h->width, h->height);
     }
-    cudaFree(h->dAccum); cudaFree(h->dRgba);
+    if (h->p2pExported && h->dAccum)
+        h->retired.push_back(h->dAccum); // a peer may still have it mapped: freed with the communicator
+    else
+        cudaFree(h->dAccum);
+    h->p2pReady = false; // the peers' tables describe the old buffer: set up again at the next reduce
+    cudaFree(h->dRgba);
     h->dAccum = newAccum;
     h->dRgba = newRgba;
     ATX_CUDA(cudaMemsetAsync(h->dAccum, 0, P * sizeof(float4), h->stream));
@@ -467,6 +496,11 @@ atx_status atx_set_tuning(atx_handle h, int key, int64_t value)
         if (value < 0 || value > 32)
             return fail(ATX_ERR_INVALID, "claim_threshold must be in [0, 32] (0 = automatic)");
         h->claimThreshold = static_cast<uint32_t>(value);
+        return ATX_OK;
+    case ATX_TUNE_REDUCE:
+        if (value < 0 || value > 1)
+            return fail(ATX_ERR_INVALID, "reduce must be 0 (peer memory when possible) or 1 (ncclAllReduce)");
+        h->reduceMode = static_cast<int>(value);
         return ATX_OK;
     default:
         return fail(ATX_ERR_INVALID, "unknown tuning key %d", key);
@@ -668,7 +702,7 @@ atx_status atx_sync(atx_handle h)
     if (atx_status s = ensure_device(h))
         return s;
     ATX_CUDA(cudaStreamSynchronize(h->stream));
-    return ATX_OK;
+    return p2p_check(h);
 }
 
 atx_status atx_last_render_ms(atx_handle h, float* out_ms)
@@ -725,7 +759,7 @@ atx_status atx_read_accum(atx_handle h, float* dst)
     const size_t bytes = static_cast<size_t>(h->width) * h->height * sizeof(float4);
     ATX_CUDA(cudaMemcpyAsync(dst, h->dAccum, bytes, cudaMemcpyDeviceToHost, h->stream));
     ATX_CUDA(cudaStreamSynchronize(h->stream));
-    return ATX_OK;
+    return p2p_check(h);
 }
 
 atx_status atx_write_accum(atx_handle h, const float* src, uint32_t next_frame_index)
@@ -1131,6 +1165,130 @@ extern "C" {
 
 // ---- multi-GPU ---------------------------------------------------------------
 
+} // extern "C"
+
+namespace
+{
+void p2p_teardown(atx_handle h, bool freeRetired)
+{
+    for (uint32_t r = 0; r < atx_launch::kP2pMaxRanks; r++)
+    {
+        if (static_cast<int>(r) != h->rank) // the own entries are the local pointers, not mappings
+        {
+            if (h->peerAccum[r])
+                cudaIpcCloseMemHandle(h->peerAccum[r]);
+            if (h->peerFlags[r])
+                cudaIpcCloseMemHandle(h->peerFlags[r]);
+        }
+        h->peerAccum[r] = nullptr;
+        h->peerFlags[r] = nullptr;
+    }
+    h->p2pReady = false;
+    if (freeRetired)
+    {
+        for (void* p : h->retired)
+            cudaFree(p);
+        h->retired.clear();
+        h->p2pExported = false;
+    }
+}
+
+// COLLECTIVE over the communicator: map every rank's accumulation buffer and flag block into this process. All
+// ranks leave with the same answer (an all-reduced "it worked for me" word): either every rank uses peer memory
+// from now on or every rank uses ncclAllReduce.
+atx_status p2p_setup(atx_handle h)
+{
+    using namespace atx_launch;
+    p2p_teardown(h, false);
+    h->p2pFailed = true; // until proven otherwise
+    const int N = h->nRanks;
+    int okLocal = (N >= 2 && N <= static_cast<int>(kP2pMaxRanks)) ? 1 : 0;
+    constexpr size_t kRec = 2 * sizeof(cudaIpcMemHandle_t);
+    if (!h->dP2pFlags)
+    {
+        ATX_CUDA(cudaMalloc(&h->dP2pFlags, kP2pFlagWords * sizeof(uint32_t)));
+        ATX_CUDA(cudaMalloc(&h->dP2pStage, kRec * (kP2pMaxRanks + 1) + 16));
+        void* e = nullptr;
+        ATX_CUDA(cudaHostAlloc(&e, sizeof(uint32_t), cudaHostAllocMapped));
+        h->hP2pError = static_cast<uint32_t*>(e);
+        *h->hP2pError = 0u;
+    }
+    ATX_CUDA(cudaMemsetAsync(h->dP2pFlags, 0, kP2pFlagWords * sizeof(uint32_t), h->stream));
+    h->p2pEpoch = 0;
+    cudaIpcMemHandle_t mineRec[2];
+    std::memset(mineRec, 0, sizeof(mineRec));
+    if (okLocal && (cudaIpcGetMemHandle(&mineRec[0], h->dAccum) != cudaSuccess || cudaIpcGetMemHandle(&mineRec[1], h->dP2pFlags) != cudaSuccess))
+    {
+        cudaGetLastError();
+        okLocal = 0;
+    }
+    h->p2pExported = true; // from here on a peer may map dAccum
+    // every rank's two handles to every rank
+    uint8_t* send = h->dP2pStage;
+    uint8_t* recv = h->dP2pStage + kRec;
+    ATX_CUDA(cudaMemcpyAsync(send, mineRec, kRec, cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = nccl().AllGather(send, recv, kRec, ncclUint8, h->comm, h->stream);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclAllGather: %s", nccl().GetErrorString(r));
+    std::vector<cudaIpcMemHandle_t> all(2 * static_cast<size_t>(std::max(N, 1)));
+    if (N <= static_cast<int>(kP2pMaxRanks))
+        ATX_CUDA(cudaMemcpyAsync(all.data(), recv, kRec * N, cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < N && okLocal; q++)
+    {
+        if (q == h->rank)
+        {
+            h->peerAccum[q] = h->dAccum;
+            h->peerFlags[q] = h->dP2pFlags;
+            continue;
+        }
+        void *a = nullptr, *f = nullptr;
+        if (cudaIpcOpenMemHandle(&a, all[2 * q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&f, all[2 * q + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+            cudaGetLastError(); // e.g. two ranks in one process, or no peer access between the devices
+            if (a)
+                cudaIpcCloseMemHandle(a);
+            okLocal = 0;
+            break;
+        }
+        h->peerAccum[q] = static_cast<float4*>(a);
+        h->peerFlags[q] = static_cast<uint32_t*>(f);
+    }
+    // agreement: min over ranks
+    int* word = reinterpret_cast<int*>(h->dP2pStage + kRec * (kP2pMaxRanks + 1));
+    ATX_CUDA(cudaMemcpyAsync(word, &okLocal, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    r = nccl().AllReduce(word, word, 1, ncclInt32, ncclMin, h->comm, h->stream);
+    if (r != ncclSuccess)
+        return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+    int okAll = 0;
+    ATX_CUDA(cudaMemcpyAsync(&okAll, word, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ATX_CUDA(cudaStreamSynchronize(h->stream));
+    if (!okAll)
+    {
+        p2p_teardown(h, false); // closes what this rank did open
+        return ATX_OK;          // p2pFailed stays set: NCCL
+    }
+    h->p2pReady = true;
+    h->p2pFailed = false;
+    return ATX_OK;
+}
+
+atx_status p2p_check(atx_handle h)
+{
+    if (h->hP2pError && *h->hP2pError)
+    {
+        const uint32_t code = *h->hP2pError;
+        *h->hP2pError = 0u;
+        return fail(ATX_ERR_NCCL, "peer-memory reduce timed out (%s): a rank of the communicator did not take part in atx_allreduce_accum",
+                    code == 1u ? "a peer never announced its buffer" : "a peer never finished its stores");
+    }
+    return ATX_OK;
+}
+} // namespace
+
+extern "C" {
+
 atx_status atx_comm_unique_id(uint8_t id[128])
 {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
@@ -1156,9 +1314,12 @@ atx_status atx_comm_init_rank(atx_handle h, int n_ranks, int rank, const uint8_t
         return fail(ATX_ERR_NCCL, "NCCL library not loadable");
     if (h->comm)
     {
+        cudaStreamSynchronize(h->stream);
+        p2p_teardown(h, true);
         nccl().CommDestroy(h->comm);
         h->comm = nullptr;
     }
+    h->p2pFailed = false;
     ncclUniqueId uid;
     std::memcpy(&uid, id, 128);
     ncclResult_t r = nccl().CommInitRank(&h->comm, n_ranks, uid, rank);
@@ -1176,6 +1337,7 @@ atx_status atx_comm_destroy(atx_handle h)
     if (h->comm && nccl().ok)
     {
         cudaStreamSynchronize(h->stream);
+        p2p_teardown(h, true);
         nccl().CommDestroy(h->comm);
     }
     h->comm = nullptr;
@@ -1192,10 +1354,54 @@ atx_status atx_allreduce_accum(atx_handle h)
         return fail(ATX_ERR_INVALID, "no communicator: call atx_comm_init_rank");
     if (!h->dAccum)
         return fail(ATX_ERR_INVALID, "no image");
+    if (atx_status s = p2p_check(h))
+        return s;
+    // one kernel over NVLink peer memory (atx_p2p.cu) when every rank could map every other rank's buffer;
+    // the set-up is collective and happens at the first reduce after atx_comm_init_rank or atx_resize
+    if (h->reduceMode == 0 && !h->p2pFailed && h->nRanks >= 2)
+    {
+        if (!h->p2pReady)
+            if (atx_status s = p2p_setup(h))
+                return s;
+        if (h->p2pReady)
+        {
+            atx_launch::P2pParams q;
+            std::memset(&q, 0, sizeof(q));
+            for (int r = 0; r < h->nRanks; r++)
+            {
+                q.accum[r] = h->peerAccum[r];
+                q.flags[r] = h->peerFlags[r];
+            }
+            ATX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&q.error), h->hP2pError, 0));
+            q.nRanks = static_cast<uint32_t>(h->nRanks);
+            q.rank = static_cast<uint32_t>(h->rank);
+            q.epoch = ++h->p2pEpoch;
+            q.count = h->width * h->height;
+            static const unsigned long long timeoutMs = []() {
+                const char* e = std::getenv("ATX_P2P_TIMEOUT_MS");
+                const long long v = e ? std::atoll(e) : 0;
+                return static_cast<unsigned long long>(v > 0 ? v : 60000);
+            }();
+            q.timeoutNs = timeoutMs * 1000000ull;
+            ATX_CUDA(atx_launch::p2p_allreduce(q, h->smCount, h->stream));
+            h->launches++;
+            h->lastReduce = 1;
+            return ATX_OK;
+        }
+    }
     const size_t count = static_cast<size_t>(h->width) * h->height * 4;
     ncclResult_t r = nccl().AllReduce(h->dAccum, h->dAccum, count, ncclFloat32, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess)
         return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+    h->lastReduce = 2;
+    return ATX_OK;
+}
+
+atx_status atx_last_reduce_kind(atx_handle h, int* out)
+{
+    if (!h || !out)
+        return fail(ATX_ERR_INVALID, "null argument");
+    *out = h->lastReduce;
     return ATX_OK;
 }
 

@@ -41,6 +41,22 @@ constexpr int kWavefrontMaxBounces = 254; // one queue counter per bounce
 size_t wavefront_bytes(uint32_t capacity);
 uint32_t wavefront_frames_per_wave(uint32_t pixels, uint32_t nFrames);
 cudaError_t render_wavefront(const atxk::RenderParams& p, void* work, uint32_t framesPerWave, uint64_t* launches, cudaStream_t s);
+// cross-GPU sum of the accumulation buffers over peer memory (atx_p2p.cu)
+constexpr uint32_t kP2pMaxRanks = 8;   // one NVSwitch domain
+constexpr uint32_t kP2pStart = 0;      // flag block of a rank: [0, 8) "render complete" per peer, [8, 16) "stores landed" per peer,
+constexpr uint32_t kP2pEnd = 8;        // [16] CTAs of the local kernel that are through
+constexpr uint32_t kP2pCtaDone = 16;
+constexpr uint32_t kP2pFlagWords = 32;
+struct P2pParams
+{
+    float4* accum[kP2pMaxRanks];    // every rank's accumulation buffer as mapped into this process (own entry: the local pointer)
+    uint32_t* flags[kP2pMaxRanks];  // every rank's flag block, likewise
+    uint32_t* error;                // mapped host word: 1 = a peer never announced its buffer, 2 = a peer never finished
+    uint32_t nRanks, rank, epoch;
+    uint32_t count;                 // float4 elements
+    unsigned long long timeoutNs;
+};
+cudaError_t p2p_allreduce(const P2pParams& q, int smCount, cudaStream_t s);
 cudaError_t primary_hits(const atxk::RenderParams& p, int32_t* out, cudaStream_t s);
 cudaError_t ray_directions(const atxk::RenderParams& p, float* out, cudaStream_t s);
 cudaError_t resolve_rgba(const float4* accum, uint32_t* rgba, uint32_t n, uint32_t divisor, cudaStream_t s);

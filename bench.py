@@ -263,6 +263,8 @@ def make_renderer(atx, name, local_rank, args=None):
             r.setTuning(atx.TUNE_CHUNK_SPHERES, args.chunk)
         if args.claim_threshold:
             r.setTuning(atx.TUNE_CLAIM_THRESHOLD, args.claim_threshold)
+        if args.reduce == "nccl":
+            r.setTuning(atx.TUNE_REDUCE, 1)
     r.onResize(W, H)
     cam.Resize(W, H)
     spheres = atx.pack_spheres(atx.traverseSceneGraph(scene.rootNode))
@@ -320,7 +322,7 @@ def secondary_workload(atx, name, local_rank, flush, steps=2, warmup=3):
     return out
 
 
-def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, warmup=3):
+def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, warmup=3, args=None):
     """A fixed job (total spp fixed) split across the ranks: frames rank+1, rank+1+world, ... on every GPU, buffers
     summed across the ranks inside the timed step; device-timed, max over ranks. The driver's own scaling curve is
     the weak-scaling headline; these lines say how much faster ONE job gets."""
@@ -328,6 +330,8 @@ def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, wa
     from ataraxia_b200.distributed import frame_partition
     desc, W, H, total_spp, bounces = WORKLOADS[name]
     r, cam, scene, spheres, mats, lights = make_renderer(atx, name, local_rank)
+    if args is not None and args.reduce == "nccl":
+        r.setTuning(atx.TUNE_REDUCE, 1)
     if world > 1:
         uid = [atx.Renderer.commUniqueId() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -355,6 +359,7 @@ def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, wa
     total_ms = sum(ms)
     acc = r.getAccumulation()
     counts_ok = bool((acc[..., 3] == total_spp).all())
+    reduce_kind = r.lastReduceKind()
     if world > 1:
         t = torch.tensor([total_ms, 0.0 if counts_ok else 1.0], device=f"cuda:{local_rank}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,7 +369,7 @@ def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, wa
     paths = float(W) * H * total_spp * steps
     return {"workload": desc, "scaling": "strong", "n_gpus": world, "spp_total": total_spp, "spp_this_rank": sh.count,
             "steps": steps, "ms_per_step": total_ms / steps, "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
-            "verified": {"sample_counts_all_ranks": counts_ok}}
+            "reduce": {0: None, 1: "peer memory", 2: "ncclAllReduce"}.get(reduce_kind), "verified": {"sample_counts_all_ranks": counts_ok}}
 
 
 def main():
@@ -382,6 +387,7 @@ def main():
     ap.add_argument("--park-threshold", type=int, default=0, help="while-while form: parked hits per warp that trigger the bounce phase")
     ap.add_argument("--claim-threshold", type=int, default=0, help="idle lanes per warp that trigger a batched pixel claim")
     ap.add_argument("--chunk", type=int, default=0, help="force the shared-memory chunk size in spheres (0 = automatic)")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "nccl"], help="cross-GPU sum: peer-memory kernel when possible, or ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -469,6 +475,7 @@ def main():
     clocks = sampler.stop()
     c = r.counters()
     form = FORMS.get(r.lastMegaKind(), "?")
+    reduce_kind = {0: None, 1: "one kernel over NVLink peer memory (two-shot, rank-ordered sums)", 2: "ncclAllReduce"}.get(r.lastReduceKind())
 
     # ---- verification of what the timed region rendered (untimed) ------------------------------------
     acc = r.getAccumulation()
@@ -541,7 +548,7 @@ def main():
     # ---- strong-scaling jobs next to the weak headline (all ranks take part) ----------------------
     strong_lines = None
     if args.workload == "c2" and not args.no_baselines and not args.spp:
-        strong_lines = {k: strong_workload(atx, k, rank, world, local_rank, flush, dist) for k in ("s2", "s4k", "s3")}
+        strong_lines = {k: strong_workload(atx, k, rank, world, local_rank, flush, dist, args=args) for k in ("s2", "s4k", "s3")}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -575,7 +582,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.workload, world, spp, len(spheres), len(lights)),
             "kernel": {"variant": args.variant, "mega_kind": args.mega_kind, "form": form, "park_threshold": args.park_threshold,
-                       "chunk": args.chunk},
+                       "chunk": args.chunk, "reduce": reduce_kind},
             "verified": all(v for k, v in verified.items() if isinstance(v, bool)), "verification": verified,
             "calibration_ms": calibration,
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,

@@ -153,9 +153,12 @@ enum {
                                    spheres from 4 frames per launch) */
     ATX_TUNE_PARK_THRESHOLD = 3 /* while-while form: parked hits per warp (1..32) that trigger the
                                    bounce phase (default 8) */,
-    ATX_TUNE_CLAIM_THRESHOLD = 4 /* idle lanes per warp (1..32) that trigger a batched claim from the
+    ATX_TUNE_CLAIM_THRESHOLD = 4,/* idle lanes per warp (1..32) that trigger a batched claim from the
                                    pixel pool; 0 (default) = per form: 32 while-while (whole 8x4
                                    tiles), 3 warp-queue, 2 two-slot packed */
+    ATX_TUNE_REDUCE = 5          /* atx_allreduce_accum: 0 (default) = one kernel over NVLink peer memory
+                                   when every rank can map every other rank's buffer, 1 = ncclAllReduce.
+                                   Must be set alike on all ranks. */
 };
 ATX_API atx_status atx_set_tuning(atx_handle h, int key, int64_t value);
 
@@ -275,9 +278,18 @@ ATX_API atx_status atx_comm_unique_id(uint8_t id[128]);
 ATX_API atx_status atx_comm_init_rank(atx_handle h, int n_ranks, int rank, const uint8_t id[128]);
 ATX_API atx_status atx_comm_destroy(atx_handle h);
 
-/* ncclAllReduce(float32, sum) of the accumulation buffer in place, on the
- * handle's stream (count = 4*width*height). .w sums to the exact total spp. */
+/* Sum of the accumulation buffers of all ranks, in place, on the handle's stream (4*width*height floats; .w sums to
+ * the exact total spp). COLLECTIVE. Default transport: ONE kernel over NVLink peer memory (atx_p2p.cu): every rank's
+ * buffer is mapped into every process (CUDA IPC, set up collectively at the first call after atx_comm_init_rank or
+ * atx_resize), rank r sums the r-th slice of all buffers in rank order and stores it to all ranks; two flag barriers
+ * in peer memory bracket it. Every rank ends with the same bits. Falls back to ncclAllReduce(float32, sum) when the
+ * buffers cannot be mapped (ranks sharing a process, no peer access) or ATX_TUNE_REDUCE = 1. A rank that never joins
+ * makes the others fail with ATX_ERR_NCCL after ATX_P2P_TIMEOUT_MS (environment, default 60000) at their next
+ * atx_sync / atx_read_accum instead of hanging. */
 ATX_API atx_status atx_allreduce_accum(atx_handle h);
+
+/* Transport the last atx_allreduce_accum used: 0 none yet, 1 peer-memory kernel, 2 ncclAllReduce. */
+ATX_API atx_status atx_last_reduce_kind(atx_handle h, int* out);
 
 /* Progressive preview across ranks: the sum of every rank's accumulation buffer into a separate preview buffer
  * (one out-of-place ncclAllReduce on the handle's stream; a device copy without a communicator). The ranks' own

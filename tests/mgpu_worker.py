@@ -43,10 +43,44 @@ def main():
     preview_ok &= bool(((prev_rgba >> 24) == 255).all())
     r.renderFrames(sh.first + half * sh.stride, sh.count - half, sh.stride, zero_first=False)
     continued = r.getAccumulation()
-    share = render_split(r, total, rank, world)          # frames rank+1, rank+1+world, ... then NCCL sum
+    share = render_split(r, total, rank, world)          # frames rank+1, rank+1+world, ... then the sum across ranks
     reduced = r.getAccumulation()
     rgba = r.getRGBA8(divisor=total)
     ok = preview_ok
+    # default transport: one kernel over NVLink peer memory (separate processes on one NVSwitch domain can always map each other)
+    p2p_ok = r.lastReduceKind() == atx.REDUCE_PEER_MEMORY
+    # the same sum through ncclAllReduce: equal up to the order of N float additions; and again through peer memory
+    # (second epoch of the flag barriers): bit-identical to the first time
+    r.setTuning(atx.TUNE_REDUCE, 1)
+    render_split(r, total, rank, world)
+    via_nccl = r.getAccumulation()
+    p2p_ok &= r.lastReduceKind() == atx.REDUCE_NCCL
+    p2p_ok &= bool((via_nccl[..., 3] == reduced[..., 3]).all()) and bool(np.allclose(via_nccl[..., :3], reduced[..., :3], rtol=1e-6, atol=1e-7))
+    r.setTuning(atx.TUNE_REDUCE, 0)
+    for _ in range(3):
+        render_split(r, total, rank, world)
+    p2p_ok &= bool((r.getAccumulation().view(np.uint32) == reduced.view(np.uint32)).all()) and r.lastReduceKind() == atx.REDUCE_PEER_MEMORY
+    # a resize replaces the accumulation buffer: the peer mappings are set up again at the next reduce
+    r.onResize(W + 32, H); cam.Resize(W + 32, H); r.setCamera(cam)
+    render_split(r, total, rank, world)
+    wide = r.getAccumulation()
+    p2p_ok &= bool((wide[..., 3] == total).all()) and r.lastReduceKind() == atx.REDUCE_PEER_MEMORY
+    r.onResize(W, H); cam.Resize(W, H); r.setCamera(cam)
+    render_split(r, total, rank, world)
+    p2p_ok &= bool((r.getAccumulation().view(np.uint32) == reduced.view(np.uint32)).all())
+    # per-rank checkpoint of an spp-split render: half of the share, save, load, rest of the share == the whole share
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        r.renderFrames(sh.first, half, sh.stride, zero_first=True)
+        path = f"{td}/rank{rank}.ckpt"
+        r.saveCheckpoint(path, next_frame_index=sh.first + half * sh.stride, frame_stride=sh.stride)
+        r.renderFrames(1, 1, 1, zero_first=True)             # clobber
+        nxt, stride = r.loadCheckpoint(path)
+        r.renderFrames(nxt, sh.count - half, stride, zero_first=False)
+        p2p_ok &= bool((r.getAccumulation().view(np.uint32) == continued.view(np.uint32)).all())
+    ok &= p2p_ok
+    if not p2p_ok:
+        print(f"rank {rank}: peer-memory reduce checks failed (last kind {r.lastReduceKind()})", flush=True)
     # the share rendered in two launches around the preview equals the share rendered in one (render_split re-renders it)
     r.renderFrames(sh.first, sh.count, sh.stride, zero_first=True)
     ok &= bool((r.getAccumulation().view(np.uint32) == continued.view(np.uint32)).all())
@@ -58,7 +92,7 @@ def main():
         ok &= bool(np.allclose(reduced[..., :3], seq[..., :3], rtol=2e-6, atol=1e-6))   # float reassociation only
         d = np.abs(((rgba >> 8) & 0xFF).astype(int) - ((rgba_seq >> 8) & 0xFF).astype(int))
         ok &= bool(d.max() <= 1)
-        print(f"MGPU world={world} total={total} share0={share.count} preview_ok={preview_ok} counts_ok={(reduced[..., 3] == total).all()} "
+        print(f"MGPU world={world} total={total} share0={share.count} preview_ok={preview_ok} p2p_ok={p2p_ok} counts_ok={(reduced[..., 3] == total).all()} "
               f"max_abs_diff={np.abs(reduced[..., :3] - seq[..., :3]).max():.3e} rgba_lsb={d.max()} ok={ok}", flush=True)
     # every rank holds the same reduced buffer
     t = torch.from_numpy(reduced.copy()).cuda()
