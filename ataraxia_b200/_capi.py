@@ -26,7 +26,7 @@ SYMBOLS = [
     "atx_comm_unique_id", "atx_comm_init_rank", "atx_comm_destroy", "atx_allreduce_accum", "atx_allreduce_preview", "atx_read_preview",
     "atx_host_camera_matrices", "atx_host_ray_directions", "atx_host_node_transform", "atx_host_transform_sphere", "atx_host_mat4_mul",
     "atx_host_camera_update",
-    "atx_save_checkpoint", "atx_load_checkpoint", "atx_scene_sha256", "atx_host_sha256", "atx_last_reduce_kind",
+    "atx_save_checkpoint", "atx_load_checkpoint", "atx_scene_sha256", "atx_host_sha256", "atx_last_reduce_kind", "atx_render_tiles", "atx_render_tile_share",
 ]
 
 ATX_OK = 0
@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         "atx_scene_sha256": [vp, C.POINTER(C.c_uint8)],
         "atx_host_sha256": [vp, C.c_size_t, C.POINTER(C.c_uint8)],
         "atx_last_reduce_kind": [vp, C.POINTER(C.c_int)],
+        "atx_render_tiles": [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int],
+        "atx_render_tile_share": [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32],
     }
     for name, argtypes in sig.items():
         fn = getattr(l, name)

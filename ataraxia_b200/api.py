@@ -575,6 +575,15 @@ class Renderer:
         return acc, rgba
     def allreduceAccum(self): check(_capi.lib().atx_allreduce_accum(self._h))
 
+    def renderTiles(self, first: int, count: int, zero_first: bool = False):
+        """Image-tile split across the communicator's ranks (atx_render_tiles): this rank renders frames first..first+count-1
+        of its interleaved 8x4 tiles and stores them into every rank's image over NVLink. Collective."""
+        check(_capi.lib().atx_render_tiles(self._h, first, count, int(zero_first), self.variant))
+
+    def renderTileShare(self, first: int, count: int, n_shares: int, share: int, zero_first: bool = False):
+        """One share of the image-tile split, locally (atx_render_tile_share)."""
+        check(_capi.lib().atx_render_tile_share(self._h, first, count, int(zero_first), self.variant, n_shares, share))
+
     def lastReduceKind(self) -> int:
         """Transport of the last allreduceAccum: REDUCE_PEER_MEMORY (one kernel over NVLink peer memory) or REDUCE_NCCL."""
         v = C.c_int()

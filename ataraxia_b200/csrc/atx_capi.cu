@@ -219,7 +219,11 @@ atx_status make_params(atx_handle h, atxk::RenderParams& p)
         chunk = fit / 2; // double-buffered
     p.chunkSpheres = chunk ? chunk : 1;
     p.parkThreshold = h->parkThreshold;
-    p.poolSize = ((h->width + 7u) / 8u) * ((h->height + 3u) / 4u) * 32u;
+    p.nTiles = ((h->width + 7u) / 8u) * ((h->height + 3u) / 4u);
+    p.tileStride = 1u;
+    p.tileOffset = 0u;
+    p.nPush = 0u;
+    p.poolSize = p.nTiles * 32u;
     p.pool = h->dPool;
     const atx::mat4& ip = h->cam.invProj;
     const atx::mat4& iv = h->cam.invView;
@@ -524,7 +528,7 @@ atx_status atx_frame_index(atx_handle h, uint32_t* out)
 }
 
 static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32_t stride, bool zeroFirst, int variant,
-                                bool emitRgba, uint32_t rgbaDivisor)
+                                bool emitRgba, uint32_t rgbaDivisor, uint32_t tileStride = 1, uint32_t tileOffset = 0, bool push = false)
 {
     if (variant != ATX_VARIANT_AUTO && variant != ATX_VARIANT_MEGAKERNEL && variant != ATX_VARIANT_WAVEFRONT)
         return fail(ATX_ERR_INVALID, "unknown variant %d", variant);
@@ -539,6 +543,18 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.zeroFirst = zeroFirst ? 1 : 0;
     p.emitRgba = emitRgba ? 1 : 0;
     p.rgbaDivisor = rgbaDivisor;
+    if (tileStride > 1u)
+    {
+        if (variant == ATX_VARIANT_WAVEFRONT)
+            return fail(ATX_ERR_INVALID, "the image-tile split needs the megakernel's pixel pool");
+        p.tileStride = tileStride;
+        p.tileOffset = tileOffset;
+        p.poolSize = ((p.nTiles + p.tileStride - 1u) / p.tileStride) * 32u;
+        if (push && h->p2pReady)
+            for (int r = 0; r < h->nRanks; r++)
+                if (r != h->rank)
+                    p.push[p.nPush++] = h->peerAccum[r];
+    }
     if (variant == ATX_VARIANT_WAVEFRONT)
     {
         h->lastKind = 0;
@@ -1274,6 +1290,37 @@ atx_status p2p_setup(atx_handle h)
     return ATX_OK;
 }
 
+unsigned long long p2p_timeout_ns()
+{
+    static const unsigned long long timeoutMs = []() {
+        const char* e = std::getenv("ATX_P2P_TIMEOUT_MS");
+        const long long v = e ? std::atoll(e) : 0;
+        return static_cast<unsigned long long>(v > 0 ? v : 60000);
+    }();
+    return timeoutMs * 1000000ull;
+}
+
+// the peer-memory kernel on the handle's stream: flag barrier, sum of `count` float4 (0: none), flag barrier
+atx_status p2p_enqueue(atx_handle h, uint32_t count)
+{
+    atx_launch::P2pParams q;
+    std::memset(&q, 0, sizeof(q));
+    for (int r = 0; r < h->nRanks; r++)
+    {
+        q.accum[r] = h->peerAccum[r];
+        q.flags[r] = h->peerFlags[r];
+    }
+    ATX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&q.error), h->hP2pError, 0));
+    q.nRanks = static_cast<uint32_t>(h->nRanks);
+    q.rank = static_cast<uint32_t>(h->rank);
+    q.epoch = ++h->p2pEpoch;
+    q.count = count;
+    q.timeoutNs = p2p_timeout_ns();
+    ATX_CUDA(atx_launch::p2p_allreduce(q, h->smCount, h->stream));
+    h->launches++;
+    return ATX_OK;
+}
+
 atx_status p2p_check(atx_handle h)
 {
     if (h->hP2pError && *h->hP2pError)
@@ -1365,26 +1412,8 @@ atx_status atx_allreduce_accum(atx_handle h)
                 return s;
         if (h->p2pReady)
         {
-            atx_launch::P2pParams q;
-            std::memset(&q, 0, sizeof(q));
-            for (int r = 0; r < h->nRanks; r++)
-            {
-                q.accum[r] = h->peerAccum[r];
-                q.flags[r] = h->peerFlags[r];
-            }
-            ATX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&q.error), h->hP2pError, 0));
-            q.nRanks = static_cast<uint32_t>(h->nRanks);
-            q.rank = static_cast<uint32_t>(h->rank);
-            q.epoch = ++h->p2pEpoch;
-            q.count = h->width * h->height;
-            static const unsigned long long timeoutMs = []() {
-                const char* e = std::getenv("ATX_P2P_TIMEOUT_MS");
-                const long long v = e ? std::atoll(e) : 0;
-                return static_cast<unsigned long long>(v > 0 ? v : 60000);
-            }();
-            q.timeoutNs = timeoutMs * 1000000ull;
-            ATX_CUDA(atx_launch::p2p_allreduce(q, h->smCount, h->stream));
-            h->launches++;
+            if (atx_status s = p2p_enqueue(h, h->width * h->height))
+                return s;
             h->lastReduce = 1;
             return ATX_OK;
         }
@@ -1394,6 +1423,90 @@ atx_status atx_allreduce_accum(atx_handle h)
     if (r != ncclSuccess)
         return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
     h->lastReduce = 2;
+    return ATX_OK;
+}
+
+// Image-tile split (the alternative to the spp split): rank r of R renders ALL requested frames of the
+// 8x4 tiles r, r + R, r + 2R, ... and its kernel stores every finished pixel straight into the image of every rank over
+// NVLink peer memory; a flag barrier in peer memory ends the step. No arithmetic happens on the wire, the per-pixel
+// prologue (primary ray, cached first bounce) is not replicated across ranks, and the sums of a pixel are formed on
+// one GPU in frame order - so the image is bit-identical to a single-GPU render of the same frames, on every rank.
+atx_status atx_render_tiles(atx_handle h, uint32_t first_frame, uint32_t n_frames, int zero_first, int variant)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    if (n_frames == 0)
+        return fail(ATX_ERR_INVALID, "n_frames must be >= 1");
+    if (atx_status s = p2p_check(h))
+        return s;
+    h->timed = false;
+    const bool multi = h->comm && h->nRanks >= 2;
+    if (multi && h->reduceMode == 0 && !h->p2pFailed && !h->p2pReady)
+        if (atx_status s = p2p_setup(h)) // collective
+            return s;
+    const bool peer = multi && h->reduceMode == 0 && h->p2pReady;
+    ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
+    const size_t P = static_cast<size_t>(h->width) * h->height;
+    if (multi && !peer)
+    {
+        // no peer mappings: keep only this rank's tiles (zero everywhere else), render, sum with ncclAllReduce: x + 0 == x,
+        // so the result is the same bits, at the price of a full all-reduce
+        if (zero_first)
+            ATX_CUDA(cudaMemsetAsync(h->dAccum, 0, P * sizeof(float4), h->stream));
+        else
+        {
+            ATX_CUDA(atx_launch::keep_own_tiles(h->dAccum, h->width, h->height, static_cast<uint32_t>(h->nRanks), static_cast<uint32_t>(h->rank), h->stream));
+            h->launches++;
+        }
+    }
+    if (peer)
+        // peers store into this rank's image while they render: nobody starts before every rank's stream has reached this
+        // step (e.g. has finished reading the previous image back)
+        if (atx_status s = p2p_enqueue(h, 0))
+            return s;
+    if (atx_status s = launch_frames(h, first_frame, n_frames, 1, zero_first != 0, variant, false, 1, multi ? static_cast<uint32_t>(h->nRanks) : 1u,
+                                     multi ? static_cast<uint32_t>(h->rank) : 0u, peer))
+        return s;
+    h->lastFrame = first_frame + n_frames - 1;
+    if (peer)
+    {
+        // the kernel's peer stores are complete when it ends; tell every rank, and wait until every rank has told us
+        if (atx_status s = p2p_enqueue(h, 0))
+            return s;
+        h->lastReduce = 1;
+    }
+    else if (multi)
+    {
+        ncclResult_t r = nccl().AllReduce(h->dAccum, h->dAccum, P * 4, ncclFloat32, ncclSum, h->comm, h->stream);
+        if (r != ncclSuccess)
+            return fail(ATX_ERR_NCCL, "ncclAllReduce: %s", nccl().GetErrorString(r));
+        h->lastReduce = 2;
+    }
+    ATX_CUDA(cudaEventRecord(h->evStop, h->stream));
+    h->timed = true;
+    return ATX_OK;
+}
+
+// one share of an image-tile split, locally: the tiles share, share + n_shares, ... of the image; every other pixel of the
+// accumulation buffer is left alone
+atx_status atx_render_tile_share(atx_handle h, uint32_t first_frame, uint32_t n_frames, int zero_first, int variant, uint32_t n_shares,
+                                 uint32_t share)
+{
+    if (atx_status s = ensure_device(h))
+        return s;
+    if (!h->dAccum)
+        return fail(ATX_ERR_INVALID, "atx_resize has not been called");
+    if (n_frames == 0 || n_shares == 0 || share >= n_shares)
+        return fail(ATX_ERR_INVALID, "n_frames >= 1 and share < n_shares are required");
+    h->timed = false;
+    ATX_CUDA(cudaEventRecord(h->evStart, h->stream));
+    if (atx_status s = launch_frames(h, first_frame, n_frames, 1, zero_first != 0, variant, false, 1, n_shares, share, false))
+        return s;
+    h->lastFrame = first_frame + n_frames - 1;
+    ATX_CUDA(cudaEventRecord(h->evStop, h->stream));
+    h->timed = true;
     return ATX_OK;
 }
 

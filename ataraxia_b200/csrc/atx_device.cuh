@@ -56,6 +56,12 @@ struct RenderParams
     uint32_t claimThreshold; // idle lanes (of 32) that trigger a batched pixel claim
     uint32_t poolSize;      // pixel ids in the pool: 8x4 tiles x 32, padded tiles included
     uint32_t* pool;         // next unclaimed id (zeroed before the launch)
+    // image-tile split across GPUs (atx_render_tiles): this rank renders the 8x4 tiles tileOffset, tileOffset +
+    // tileStride, ... (the pool holds only those) and stores every finished pixel into the image of EVERY rank:
+    // its own (accum) and the peers' buffers mapped over NVLink (push[0 .. nPush))
+    uint32_t tileStride, tileOffset, nTiles;
+    uint32_t nPush;
+    float4* push[7];
     const float4* spheres;    // (-cx, -cy, -cz, r): the exact tests, hit records
     const float4* sphFilter;  // (-cx, -cy, -cz, |c|^2 - r^2 - margin): the packed line filter (filter_sphere)
     const int32_t* sphMat;
@@ -529,6 +535,15 @@ ATX_DEV bool path_bounce(const RenderParams& p, PathState& s)
         return true;
     s.seed += static_cast<uint32_t>(s.bounce); // Renderer.cu:306
     return false;
+}
+
+// the finished sums of a pixel: st.global.v4.f32 into the local image and, with an image-tile split, into every
+// peer's image over NVLink (the transfer rides along with the rendering, pixel by pixel)
+ATX_DEV void store_pixel(const RenderParams& p, uint32_t pixel, const float4 acc)
+{
+    p.accum[pixel] = acc;
+    for (uint32_t r = 0; r < p.nPush; r++)
+        p.push[r][pixel] = acc;
 }
 
 // accumulation[p] += vec4(color, 1)   (Renderer.cu:165, :386)

@@ -255,10 +255,10 @@ __device__ __forceinline__ void thread_pixel(uint32_t& x, uint32_t& y)
 __device__ __forceinline__ bool pool_pixel(const RenderParams& p, uint32_t id, uint32_t& x, uint32_t& y)
 {
     const uint32_t tilesX = (p.width + 7u) >> 3;
-    const uint32_t tile = id >> 5, w = id & 31u;
+    const uint32_t tile = (id >> 5) * p.tileStride + p.tileOffset, w = id & 31u; // (stride 1, offset 0 unless the image is split across GPUs)
     x = (tile % tilesX) * 8u + (w & 7u);
     y = (tile / tilesX) * 4u + (w >> 3);
-    return x < p.width && y < p.height;
+    return tile < p.nTiles && x < p.width && y < p.height;
 }
 
 // warp-aggregated claim: one atomic per warp; returns this lane's id (valid where need is set)
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
     };
     // the pixel is complete: st.global.v4.f32 of the running sum (+ the display pack)
     auto retire = [&]() {
-        p.accum[pixel] = acc;
+        store_pixel(p, pixel, acc);
         if (p.emitRgba)
             p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
         paths += j;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
         }
         if (store)
         {
-            p.accum[pixel] = acc;
+            store_pixel(p, pixel, acc);
             if (p.emitRgba)
                 p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
             paths += p.nFrames;
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             if (live && head >= p.nFrames)
             {
                 // every frame of the pixel is in the sum: st.global.v4.f32 + the display pack
-                p.accum[pixel] = acc;
+                store_pixel(p, pixel, acc);
                 if (p.emitRgba)
                     p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
                 paths += p.nFrames;
@@ -1090,7 +1090,7 @@ struct Slot
 
 __device__ __forceinline__ void slot_retire(const RenderParams& p, Slot& t, uint32_t& paths)
 {
-    p.accum[t.pixel] = t.acc;
+    store_pixel(p, t.pixel, t.acc);
     if (p.emitRgba)
         p.rgba[t.pixel] = pack_rgba8(t.acc, u32_to_f32_rn(p.rgbaDivisor));
     paths += t.j;

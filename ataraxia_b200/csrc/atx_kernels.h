@@ -56,7 +56,8 @@ struct P2pParams
     uint32_t count;                 // float4 elements
     unsigned long long timeoutNs;
 };
-cudaError_t p2p_allreduce(const P2pParams& q, int smCount, cudaStream_t s);
+cudaError_t p2p_allreduce(const P2pParams& q, int smCount, cudaStream_t s); // count == 0: the two flag barriers only
+cudaError_t keep_own_tiles(float4* accum, uint32_t width, uint32_t height, uint32_t stride, uint32_t offset, cudaStream_t s);
 cudaError_t primary_hits(const atxk::RenderParams& p, int32_t* out, cudaStream_t s);
 cudaError_t ray_directions(const atxk::RenderParams& p, float* out, cudaStream_t s);
 cudaError_t resolve_rgba(const float4* accum, uint32_t* rgba, uint32_t n, uint32_t divisor, cudaStream_t s);

@@ -127,10 +127,30 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const atx_launch::P2
     }
 }
 
+// fallback of the image-tile split without peer mappings: zero every pixel whose 8x4 tile belongs to another rank, so
+// that a plain sum across ranks rebuilds the image
+__global__ void keep_own_tiles_kernel(float4* accum, uint32_t width, uint32_t height, uint32_t stride, uint32_t offset)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height)
+        return;
+    const uint32_t x = i % width, y = i / width;
+    const uint32_t tile = (y >> 2) * ((width + 7u) >> 3) + (x >> 3);
+    if (tile % stride != offset)
+        accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 } // namespace atxk
 
 namespace atx_launch
 {
+cudaError_t keep_own_tiles(float4* accum, uint32_t width, uint32_t height, uint32_t stride, uint32_t offset, cudaStream_t s)
+{
+    const uint32_t n = width * height;
+    atxk::keep_own_tiles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(accum, width, height, stride, offset);
+    return cudaGetLastError();
+}
+
 cudaError_t p2p_allreduce(const P2pParams& q, int smCount, cudaStream_t s)
 {
     if (q.nRanks < 1 || q.nRanks > kP2pMaxRanks)

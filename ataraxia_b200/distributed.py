@@ -32,3 +32,22 @@ def render_split(renderer, total_frames: int, rank: int, world: int, reduce: boo
     if reduce and world > 1:
         renderer.allreduceAccum()
     return share
+
+
+def tile_owner(x: int, y: int, width: int, world: int) -> int:
+    """Image-tile split (atx_render_tiles): the rank that renders pixel (x, y). Tiles are 8x4 pixels, numbered row-major,
+    and dealt to the ranks round-robin."""
+    tiles_x = (width + 7) // 8
+    return ((y // 4) * tiles_x + (x // 8)) % world
+
+
+def tile_mask(width: int, height: int, world: int, rank: int):
+    """Boolean (height, width) mask of the pixels rank `rank` of `world` renders under the image-tile split."""
+    import numpy as np
+    ys, xs = np.mgrid[0:height, 0:width]
+    return ((ys // 4) * ((width + 7) // 8) + (xs // 8)) % world == rank
+
+
+def render_tiles(renderer, first_frame: int, n_frames: int, zero_first: bool = True) -> None:
+    """Collective: every rank renders all n_frames of its tiles and stores them into every rank's image (NVLink peer stores)."""
+    renderer.renderTiles(first_frame, n_frames, zero_first)

@@ -101,11 +101,11 @@ def scene_file(name, tmpdir, atx=None):
     return path
 
 
-def config_dict(name, world, spp, n_spheres, n_lights):
+def config_dict(name, world, spp, n_spheres, n_lights, split="spp"):
     """The workload description both arms print (identical keys and values)."""
     desc, W, H, _, bounces = WORKLOADS[name]
     return {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "max_bounces": bounces,
-            "spheres": int(n_spheres), "lights": int(n_lights), "parallelism": f"spp-split x{world}",
+            "spheres": int(n_spheres), "lights": int(n_lights), "parallelism": f"{split}-split x{world}",
             "l2": "GPU arm: flushed between steps (256 MB write)"}
 
 
@@ -322,7 +322,7 @@ def secondary_workload(atx, name, local_rank, flush, steps=2, warmup=3):
     return out
 
 
-def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, warmup=3, args=None):
+def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, warmup=3, args=None, split="spp"):
     """A fixed job (total spp fixed) split across the ranks: frames rank+1, rank+1+world, ... on every GPU, buffers
     summed across the ranks inside the timed step; device-timed, max over ranks. The driver's own scaling curve is
     the weak-scaling headline; these lines say how much faster ONE job gets."""
@@ -338,11 +338,16 @@ def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, wa
         r.commInitRank(world, rank, uid[0])
     sh = frame_partition(total_spp, rank, world)
 
+    tiles = split == "tiles"
+
     def step():
         r.eventRecord(0)
-        r.renderFrames(sh.first, sh.count, sh.stride, zero_first=True)
-        if world > 1:
-            r.allreduceAccum()
+        if tiles:
+            r.renderTiles(1, total_spp, zero_first=True)
+        else:
+            r.renderFrames(sh.first, sh.count, sh.stride, zero_first=True)
+            if world > 1:
+                r.allreduceAccum()
         r.eventRecord(1)
 
     for _ in range(warmup):
@@ -367,7 +372,7 @@ def strong_workload(atx, name, rank, world, local_rank, flush, dist, steps=3, wa
         r.commDestroy()
     r.close()
     paths = float(W) * H * total_spp * steps
-    return {"workload": desc, "scaling": "strong", "n_gpus": world, "spp_total": total_spp, "spp_this_rank": sh.count,
+    return {"workload": desc, "scaling": "strong", "n_gpus": world, "split": split, "spp_total": total_spp, "spp_this_rank": total_spp if tiles else sh.count,
             "steps": steps, "ms_per_step": total_ms / steps, "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
             "reduce": {0: None, 1: "peer memory", 2: "ncclAllReduce"}.get(reduce_kind), "verified": {"sample_counts_all_ranks": counts_ok}}
 
@@ -387,6 +392,9 @@ def main():
     ap.add_argument("--park-threshold", type=int, default=0, help="while-while form: parked hits per warp that trigger the bounce phase")
     ap.add_argument("--claim-threshold", type=int, default=0, help="idle lanes per warp that trigger a batched pixel claim")
     ap.add_argument("--chunk", type=int, default=0, help="force the shared-memory chunk size in spheres (0 = automatic)")
+    ap.add_argument("--split", default="spp", choices=["spp", "tiles"],
+                    help="multi-GPU partitioning: spp = every rank renders its own frame indices of the whole image, buffers summed; "
+                         "tiles = every rank renders all frames of its interleaved 8x4 tiles and stores them into every rank's image")
     ap.add_argument("--reduce", default="auto", choices=["auto", "nccl"], help="cross-GPU sum: peer-memory kernel when possible, or ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -414,7 +422,7 @@ def main():
         line = {"impl": "reference", "metric": "Mpaths/s", "value": res["value"], "unit": "Mpaths/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args.workload, world, spp, res["spheres"], res["lights"]),
+                "config": config_dict(args.workload, world, spp, res["spheres"], res["lights"], args.split),
                 "cpu_baseline": {"value": res["value"], "unit": "Mpaths/s", "cores": res["cores"], "kind": res["kind"],
                                  "sample": res["sample"]},
                 "e2e": {"value": res["value"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -445,12 +453,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def render_share():
+        if args.split == "tiles":
+            # all total_spp frames of this rank's tiles, stored into every rank's image over NVLink while rendering
+            r.renderTiles(1, total_spp, zero_first=True)
+        else:
+            # rank's share of the total_spp-spp image: frame indices rank+1, rank+1+world, ...; buffers summed across ranks
+            r.renderFrames(rank + 1, spp, world, zero_first=True)
+            if world > 1:
+                r.allreduceAccum()
+
     def step():
-        # rank's share of the total_spp-spp image: frame indices rank+1, rank+1+world, ...
         r.eventRecord(0)
-        r.renderFrames(rank + 1, spp, world, zero_first=True)
-        if world > 1:
-            r.allreduceAccum()
+        render_share()
         r.eventRecord(1)
 
     calibration = None
@@ -497,7 +512,10 @@ def main():
             seq = r.getAccumulation()
             err = np.abs(acc[..., :3] - seq[..., :3]) / np.maximum(np.abs(seq[..., :3]), 1e-3)
             verified["reduced_vs_sequential_max_rel"] = float(err.max())
-            verified["reduced_vs_sequential"] = bool(err.max() <= 2e-6 * total_spp ** 0.5 + 2e-6)
+            if args.split == "tiles":   # every pixel summed on one GPU in frame order: the single-GPU bits
+                verified["tiles_bit_identical_to_sequential"] = bool((acc.view(np.uint32) == seq.view(np.uint32)).all())
+            else:                       # N partial sums added in rank order: float reassociation only
+                verified["reduced_vs_sequential"] = bool(err.max() <= 2e-6 * total_spp ** 0.5 + 2e-6)
         ok = torch.tensor([0.0 if verified["sample_counts"] else 1.0], device=f"cuda:{local_rank}")
         dist.all_reduce(ok, op=dist.ReduceOp.MAX)
         verified["sample_counts"] = float(ok.item()) == 0.0
@@ -526,9 +544,7 @@ def main():
     def e2e_step():
         r.uploadArrays(hs.numpy().view(atx.SPHERE_DTYPE), hm.numpy().view(atx.MATERIAL_DTYPE), hl.numpy().view(atx.LIGHT_DTYPE))
         r.setCamera(cam)
-        r.renderFrames(rank + 1, spp, world, zero_first=True)
-        if world > 1:
-            r.allreduceAccum()
+        render_share()
         r.getRGBA8(divisor=total_spp, out=rgba_np)   # resolve + D2H; waits for the stream
 
     e2e_step()
@@ -548,7 +564,8 @@ def main():
     # ---- strong-scaling jobs next to the weak headline (all ranks take part) ----------------------
     strong_lines = None
     if args.workload == "c2" and not args.no_baselines and not args.spp:
-        strong_lines = {k: strong_workload(atx, k, rank, world, local_rank, flush, dist, args=args) for k in ("s2", "s4k", "s3")}
+        strong_lines = {f"{k}_{sp}": strong_workload(atx, k, rank, world, local_rank, flush, dist, args=args, split=sp)
+                        for k in ("s2", "s4k", "s3") for sp in (("tiles", "spp") if world > 1 else ("spp",))}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -580,7 +597,7 @@ def main():
             "metric": "Mpaths/s", "value": paths / (total_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.workload, world, spp, len(spheres), len(lights)),
+            "config": config_dict(args.workload, world, spp, len(spheres), len(lights), args.split),
             "kernel": {"variant": args.variant, "mega_kind": args.mega_kind, "form": form, "park_threshold": args.park_threshold,
                        "chunk": args.chunk, "reduce": reduce_kind},
             "verified": all(v for k, v in verified.items() if isinstance(v, bool)), "verification": verified,

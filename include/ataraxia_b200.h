@@ -288,7 +288,25 @@ ATX_API atx_status atx_comm_destroy(atx_handle h);
  * atx_sync / atx_read_accum instead of hanging. */
 ATX_API atx_status atx_allreduce_accum(atx_handle h);
 
-/* Transport the last atx_allreduce_accum used: 0 none yet, 1 peer-memory kernel, 2 ncclAllReduce. */
+/* Image-tile split (the alternative to the spp split). COLLECTIVE. Rank r of R renders ALL of the frames
+ * first_frame .. first_frame + n_frames - 1 for the 8x4-pixel tiles r, r + R, r + 2R, ... (row-major tile order: a
+ * fine interleave, so sky and geometry spread evenly), and its kernel stores every finished pixel into the image of
+ * EVERY rank over NVLink peer memory while it renders; flag barriers in peer memory open and close the step. No
+ * arithmetic on the wire and each pixel is summed on one GPU in frame order: every rank ends with an image that is
+ * bit-identical to a single-GPU atx_render_frames(first_frame, n_frames, 1, zero_first). With zero_first = 0 the
+ * frames are added to the image every rank already holds (all ranks must hold the same one: the result of an earlier
+ * atx_render_tiles or atx_allreduce_accum). Without peer mappings (see atx_allreduce_accum) the ranks' tiles are
+ * combined with ncclAllReduce instead (same bits, more traffic). Without a communicator it renders the whole image. */
+ATX_API atx_status atx_render_tiles(atx_handle h, uint32_t first_frame, uint32_t n_frames, int zero_first, int variant);
+
+/* One share of an image-tile split rendered locally, no communication: the 8x4 tiles share, share + n_shares, ... of
+ * the image get the frames first_frame .. first_frame + n_frames - 1 (zero_first: starting from zero instead of the
+ * stored sums); every other pixel of the accumulation buffer is left untouched. The shares 0 .. n_shares-1 together
+ * are bit-identical to one atx_render_frames of the whole image. */
+ATX_API atx_status atx_render_tile_share(atx_handle h, uint32_t first_frame, uint32_t n_frames, int zero_first, int variant,
+                                         uint32_t n_shares, uint32_t share);
+
+/* Transport the last atx_allreduce_accum / atx_render_tiles used: 0 none yet, 1 peer memory, 2 ncclAllReduce. */
 ATX_API atx_status atx_last_reduce_kind(atx_handle h, int* out);
 
 /* Progressive preview across ranks: the sum of every rank's accumulation buffer into a separate preview buffer

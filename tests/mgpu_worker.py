@@ -78,6 +78,22 @@ def main():
         nxt, stride = r.loadCheckpoint(path)
         r.renderFrames(nxt, sh.count - half, stride, zero_first=False)
         p2p_ok &= bool((r.getAccumulation().view(np.uint32) == continued.view(np.uint32)).all())
+    # image-tile split: every rank renders ALL frames of its interleaved 8x4 tiles and stores them into every rank's image over
+    # NVLink while rendering; the image is bit-identical to a single-GPU render, on every rank, also when continuing
+    r.renderTiles(1, total, zero_first=True)
+    tiles1 = r.getAccumulation()
+    tile_kind = r.lastReduceKind()
+    r.renderTiles(total + 1, 3, zero_first=False)
+    tiles2 = r.getAccumulation()
+    r.renderFrames(1, total, 1, zero_first=True)
+    p2p_ok &= bool((r.getAccumulation().view(np.uint32) == tiles1.view(np.uint32)).all()) and tile_kind == atx.REDUCE_PEER_MEMORY
+    r.renderFrames(total + 1, 3, 1, zero_first=False)
+    p2p_ok &= bool((r.getAccumulation().view(np.uint32) == tiles2.view(np.uint32)).all())
+    r.setTuning(atx.TUNE_REDUCE, 1)                         # without peer mappings: own tiles kept, the rest zeroed, ncclAllReduce
+    r.renderTiles(1, total, zero_first=True)
+    r.renderTiles(total + 1, 3, zero_first=False)
+    p2p_ok &= bool((r.getAccumulation().view(np.uint32) == tiles2.view(np.uint32)).all()) and r.lastReduceKind() == atx.REDUCE_NCCL
+    r.setTuning(atx.TUNE_REDUCE, 0)
     ok &= p2p_ok
     if not p2p_ok:
         print(f"rank {rank}: peer-memory reduce checks failed (last kind {r.lastReduceKind()})", flush=True)

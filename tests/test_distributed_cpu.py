@@ -63,3 +63,18 @@ def test_spp_split_allreduce_world2(built, port, tmp_path, total):
     rgba_b = port.pack_rgba8(seq, total)
     diff = np.abs(((rgba_a >> 8) & 0xFF).astype(int) - ((rgba_b >> 8) & 0xFF).astype(int))
     assert diff.max() <= 1                                                    # at most 1 LSB in the display image
+
+
+def test_tile_partition_covers_every_pixel_once():
+    """Image-tile split (atx_render_tiles): 8x4 tiles dealt round-robin; every pixel has exactly one owner, the shares
+    are balanced to within one tile, and tile_owner agrees with tile_mask."""
+    import numpy as np
+    from ataraxia_b200.distributed import tile_mask, tile_owner
+    for W, H in ((1920, 1080), (161, 91), (8, 4), (7, 3)):
+        for world in (1, 2, 3, 8):
+            masks = [tile_mask(W, H, world, r) for r in range(world)]
+            assert (sum(m.astype(int) for m in masks) == 1).all()
+            tiles = [len({(y // 4, x // 8) for y, x in zip(*np.nonzero(m))}) for m in masks]
+            assert max(tiles) - min(tiles) <= 1
+            for (x, y) in ((0, 0), (W - 1, H - 1), (W // 2, H // 3)):
+                assert masks[tile_owner(x, y, W, world)][y, x]

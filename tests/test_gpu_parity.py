@@ -472,6 +472,37 @@ def test_config5_geometry_8k(atx):
     r.close()
 
 
+def test_tile_shares_cover_the_image_bit_identically(atx):
+    """Image-tile split on one GPU (the multi-GPU form pushes the same shares over NVLink, tests/mgpu_worker.py): the
+    shares 0..R-1 of a render, launched one after the other into the same buffer, are the one-launch image bit for bit;
+    a share touches only its own 8x4 tiles (ataraxia_b200.distributed.tile_mask); odd sizes with partial tiles; every
+    megakernel form; continuing stored sums."""
+    from ataraxia_b200.distributed import tile_mask
+    cases = [(atx.Utils.importScene(str(GOLDEN / "sample_scene.json")), 161, 91, 8, 12, (3, 8), (atx.MEGA_AUTO, atx.MEGA_WHILE_WHILE)),
+             (atx.synthetic.small(40, 3, seed=21), 200, 110, 6, 6, (2, 5), (atx.MEGA_PAIR, atx.MEGA_PAIR_LOCKSTEP))]
+    for scene, W, H, bounces, frames, worlds, kinds in cases:
+        r, cam = setup(atx, scene, W, H, bounces, True)
+        r.uploadScene(scene); r.setCamera(cam)
+        r.renderFrames(1, frames, 1, zero_first=True)
+        r.renderFrames(frames + 1, 3, 1, zero_first=False)
+        want = r.getAccumulation()
+        for kind in kinds:
+            r.setTuning(atx.TUNE_MEGA_KIND, kind)
+            for world in worlds:
+                r.renderFrames(1, 0, 1, zero_first=True)                        # clear
+                for rank in range(world):
+                    r.renderTileShare(1, frames, world, rank, zero_first=(rank % 2 == 0))   # zero_first or adding to zeros: same
+                    acc = r.getAccumulation()
+                    done = np.zeros((H, W), bool)
+                    for q in range(rank + 1):
+                        done |= tile_mask(W, H, world, q)
+                    assert (acc[..., 3][done] == frames).all() and (acc[~done] == 0).all(), (kind, world, rank)
+                for rank in reversed(range(world)):
+                    r.renderTileShare(frames + 1, 3, world, rank, zero_first=False)
+                assert (bits(r.getAccumulation()) == bits(want)).all(), (kind, world)
+        r.close()
+
+
 def test_spp_split_sums_to_sequential(atx):
     """Rank-style frame split (first, stride) into zeroed buffers, summed on the host."""
     from ataraxia_b200.distributed import frame_partition
