@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
 out=ataraxia_b200/lib/variants; mkdir -p $out/obj_$name
-for f in atx_capi atx_kernels atx_wavefront; do
+for f in atx_capi atx_kernels atx_wavefront atx_p2p; do
   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -ftz=true -prec-div=false -prec-sqrt=false "$@" \
        -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden -Iinclude -c ataraxia_b200/csrc/$f.cu -o $out/obj_$name/$f.o &
 done
