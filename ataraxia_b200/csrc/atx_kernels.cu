@@ -88,9 +88,12 @@ __global__ void pack_scene_kernel(const float* __restrict__ sphAoS, uint32_t nSp
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t round_up8(uint32_t n) { return (n + 7u) & ~7u; }
 
-__device__ __forceinline__ void stage_spheres(float4* dst, const float4* __restrict__ src, uint32_t count)
+__device__ __forceinline__ uint32_t round_up32(uint32_t n) { return (n + 31u) & ~31u; }
+
+// pad = 8 (scalar forms) or 32 (packed forms: whole blocks of 32 filter steps)
+__device__ __forceinline__ void stage_spheres(float4* dst, const float4* __restrict__ src, uint32_t count, uint32_t pad = 8u)
 {
-    const uint32_t padded = round_up8(count);
+    const uint32_t padded = (count + pad - 1u) & ~(pad - 1u);
     for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x)
         dst[i] = i < count ? __ldg(src + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
@@ -135,7 +138,7 @@ __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, u
 }
 
 // packed: the two rays of a thread against the filter records of spheres [0, count) resident at `sph`
-// (shared memory, padded to a multiple of 8); `exact` is the global array of exact records (indexed from
+// (shared memory, padded to a multiple of 32); `exact` is the global array of exact records (indexed from
 // base: the few candidates of a lane are read through L1). Two stages per super-block of up to kSuperBlock spheres:
 //   filter   blocks of 32 spheres, branch-free: two 32-bit candidate words per block go to this
 //            thread's private column of `cand` (shared memory, conflict-free), plus one bit per
@@ -159,39 +162,40 @@ __device__ __forceinline__ void trace_range2(const float4* sph, const float4* __
                                              float& tmin0, int& closest0, float& tmin1, int& closest1)
 {
     uint32_t* mine = cand + threadIdx.x; // word w of this thread: mine[w * blockDim.x]
+    const uint32_t T = blockDim.x;
     for (uint32_t sb = 0; sb < count; sb += kSuperBlock)
     {
         const uint32_t sbCount = min(kSuperBlock, count - sb);
         const uint32_t nBlocks = (sbCount + 31u) >> 5;
         uint32_t nz0 = 0u, nz1 = 0u;
         const float4* q = sph + sb;
+        uint32_t* w = mine;
+        // whole blocks of 32 filter steps, straight-line: the resident array is padded to a multiple of 32, and whatever the
+        // padding records answer is masked out of the last block below
 #pragma unroll 1
-        for (uint32_t blk = 0; blk < nBlocks; blk++)
+        for (uint32_t blk = 0; blk < nBlocks; blk++, q += 32, w += 2u * T)
         {
-            const uint32_t cnt = min(32u, sbCount - blk * 32u);
-            const uint32_t groups = (cnt + 7u) >> 3;
             uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll 1
-            for (uint32_t g = 0; g < groups; g++, q += 8)
-            {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    filter_sphere(q[i], rp, m0, m1);
-            }
-            uint32_t c0 = ~m0, c1 = ~m1;
-            if (cnt < 32u)
-            {
-                // sphere i of the block sits at bit (8*groups-1-i): left-align so it is bit (31-i),
-                // and drop the zero-padded tail
-                const uint32_t sh = 32u - 8u * groups;
-                const uint32_t valid = 0xFFFFFFFFu << (32u - cnt);
-                c0 = (c0 << sh) & valid;
-                c1 = (c1 << sh) & valid;
-            }
-            mine[(2u * blk) * blockDim.x] = c0;
-            mine[(2u * blk + 1u) * blockDim.x] = c1;
-            nz0 = (nz0 << 1) | (c0 != 0u ? 1u : 0u);
-            nz1 = (nz1 << 1) | (c1 != 0u ? 1u : 0u);
+            for (int i = 0; i < 32; i++)
+                filter_sphere(q[i], rp, m0, m1);
+            // sphere i of the block sits at bit (31 - i); a clear sign bit made it a candidate
+            const uint32_t c0 = ~m0, c1 = ~m1;
+            w[0] = c0;
+            w[T] = c1;
+            nz0 = (nz0 << 1) | min(c0, 1u);
+            nz1 = (nz1 << 1) | min(c1, 1u);
+        }
+        if (sbCount & 31u)
+        {
+            // the last block is partial: drop the padded tail from its two words
+            const uint32_t valid = 0xFFFFFFFFu << (32u - (sbCount & 31u));
+            uint32_t* wl = mine + 2u * (nBlocks - 1u) * T;
+            const uint32_t c0 = wl[0] & valid, c1 = wl[T] & valid;
+            wl[0] = c0;
+            wl[T] = c1;
+            nz0 = (nz0 & ~1u) | min(c0, 1u);
+            nz1 = (nz1 & ~1u) | min(c1, 1u);
         }
         // block blk at bit (31 - blk); a retired slot has no candidates
         nz0 = live0 ? nz0 << (32u - nBlocks) : 0u;
@@ -203,13 +207,13 @@ __device__ __forceinline__ void trace_range2(const float4* sph, const float4* __
             {
                 b0 = __clz(nz0);
                 nz0 &= ~(0x80000000u >> b0);
-                cur0 = mine[(2u * b0) * blockDim.x];
+                cur0 = mine[(2u * b0) * T];
             }
             if (cur1 == 0u && nz1 != 0u)
             {
                 b1 = __clz(nz1);
                 nz1 &= ~(0x80000000u >> b1);
-                cur1 = mine[(2u * b1 + 1u) * blockDim.x];
+                cur1 = mine[(2u * b1 + 1u) * T];
             }
             if ((cur0 | cur1) == 0u)
                 break;
@@ -1244,7 +1248,7 @@ __device__ __forceinline__ void trace_pair(const RenderParams& p, const float4* 
         // double-buffered chunk walk: one thread starts the bulk copy (TMA) of chunk c+1 while the CTA
         // traces chunk c; the copy signals an mbarrier, the CTA barrier at the end of an iteration says
         // "everyone is done with this buffer", which is what lets the next copy overwrite it
-        const uint32_t C = p.chunkSpheres, stride = round_up8(C);
+        const uint32_t C = p.chunkSpheres, stride = round_up32(C);
         const uint32_t nChunks = (p.nSpheres + C - 1) / C;
         float4* buf = const_cast<float4*>(sphS);
         if (threadIdx.x == 0)
@@ -1275,12 +1279,12 @@ __global__ void __launch_bounds__(256, 2) megakernel_pair(const RenderParams p)
     uint32_t phase = 0u; // parity of the next completion of each mbarrier
 
     if (!kChunked)
-        stage_spheres(sphS, p.sphFilter, p.nSpheres);
+        stage_spheres(sphS, p.sphFilter, p.nSpheres, 32u);
     else
     {
         // the padded tail of a buffer is masked out of the candidate set, never tested; zero it once so
         // no uninitialised shared memory is ever read
-        const uint32_t words = 2u * round_up8(p.chunkSpheres);
+        const uint32_t words = 2u * round_up32(p.chunkSpheres);
         for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
             sphS[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (threadIdx.x == 0)
@@ -1467,10 +1471,10 @@ __global__ void __launch_bounds__(kLsThreads, kLsCtas) megakernel_pair_ls(const 
     uint32_t phase = 0u;
 
     if (!kChunked)
-        stage_spheres(sphS, p.sphFilter, p.nSpheres);
+        stage_spheres(sphS, p.sphFilter, p.nSpheres, 32u);
     else
     {
-        const uint32_t words = 2u * round_up8(p.chunkSpheres);
+        const uint32_t words = 2u * round_up32(p.chunkSpheres);
         for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
             sphS[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (threadIdx.x == 0)
@@ -1630,10 +1634,10 @@ static size_t warp_queue_smem_bytes(const RenderParams& p)
 size_t megakernel_smem_bytes(const RenderParams& p)
 {
     const bool chunked = p.chunkSpheres < p.nSpheres;
-    const size_t pad8 = (static_cast<size_t>(chunked ? p.chunkSpheres : p.nSpheres) + 7u) & ~size_t(7);
+    const size_t pad = (static_cast<size_t>(chunked ? p.chunkSpheres : p.nSpheres) + 31u) & ~size_t(31); // whole blocks of 32 filter steps
     // the two-slot forms also keep cand_words() candidate words per thread (sized for the largest CTA of the forms)
     const uint32_t threads = kLsThreads > 256u ? kLsThreads : 256u;
-    return sizeof(float4) * (1 + (chunked ? 2 * pad8 : pad8)) + sizeof(uint32_t) * cand_words(p) * threads; // +16 B: two mbarriers
+    return sizeof(float4) * (1 + (chunked ? 2 * pad : pad)) + sizeof(uint32_t) * cand_words(p) * threads; // +16 B: two mbarriers
 }
 
 cudaError_t configure()
