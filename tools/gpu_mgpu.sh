@@ -5,7 +5,7 @@ mkdir -p gpurun_out/$tag
 export ATX_P2P_TIMEOUT_MS=20000
 timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -15
 for red in auto nccl tiles; do
-  extra="--reduce $red"; [ "$red" = "tiles" ] && extra="--split tiles"
+  extra="--reduce $red --no-baselines"; [ "$red" = "tiles" ] && extra="--split tiles --no-baselines"; [ "$red" = "auto" ] && extra=""
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 $extra "$@" > gpurun_out/$tag/bench_n${n}_$red.json 2> gpurun_out/$tag/bench_n${n}_$red.err
   tail -1 gpurun_out/$tag/bench_n${n}_$red.json | python -c "
 import sys,json
