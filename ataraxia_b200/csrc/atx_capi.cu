@@ -137,6 +137,7 @@ struct atx_renderer
     float* dRays = nullptr;
     unsigned long long* dCounters = nullptr;
     uint32_t* dPool = nullptr;  // pixel-pool counter of the persistent megakernels
+    float4* dPixelCache = nullptr; // per-pixel launch constants of the warp-queue form (lazily allocated, 96 B per pixel)
     void* dWave = nullptr;      // wavefront variant: path records, samples, queues (lazily allocated)
     size_t waveBytes = 0;
     int autoVariant = ATX_VARIANT_MEGAKERNEL; // what ATX_VARIANT_AUTO resolves to (atx_calibrate)
@@ -315,7 +316,7 @@ atx_status atx_destroy(atx_handle h)
     cudaFree(h->dP2pFlags); cudaFree(h->dP2pStage);
     if (h->hP2pError)
         cudaFreeHost(h->hP2pError);
-    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave);
+    cudaFree(h->dAccum); cudaFree(h->dRgba); cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dCounters); cudaFree(h->dPool); cudaFree(h->dWave); cudaFree(h->dPixelCache);
     cudaFree(h->dSphAoS); cudaFree(h->dMatAoS); cudaFree(h->dLightAoS);
     cudaFree(h->dSpheres); cudaFree(h->dSphFilter); cudaFree(h->dMats); cudaFree(h->dLights); cudaFree(h->dSphMat);
     cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
@@ -338,8 +339,8 @@ atx_status atx_resize(atx_handle h, uint32_t width, uint32_t height)
     ATX_CUDA(cudaStreamSynchronize(h->stream));
     // the size-dependent scratch goes first (it is re-created on demand), then the new image is allocated BEFORE the
     // old one is given up: a failed allocation leaves the handle exactly as it was (old size, old buffers)
-    cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dWave);
-    h->dPreview = nullptr; h->dHit = nullptr; h->dRays = nullptr; h->dWave = nullptr;
+    cudaFree(h->dPreview); cudaFree(h->dHit); cudaFree(h->dRays); cudaFree(h->dWave); cudaFree(h->dPixelCache);
+    h->dPreview = nullptr; h->dHit = nullptr; h->dRays = nullptr; h->dWave = nullptr; h->dPixelCache = nullptr;
     h->waveBytes = 0;
     const size_t P = static_cast<size_t>(width) * height;
     float4* newAccum = nullptr;
@@ -587,6 +588,14 @@ static atx_status launch_frames(atx_handle h, uint32_t first, uint32_t n, uint32
     p.claimThreshold = h->claimThreshold ? h->claimThreshold
                                          : (formKind == atx_launch::kMegaWhileWhile ? 32u : formKind == atx_launch::kMegaWarpQueue ? 3u : 2u);
     h->lastKind = formKind;
+    if (formKind == atx_launch::kMegaWarpQueue && p.nLights <= 1u)
+    {
+        if (!h->dPixelCache)
+            ATX_CUDA(cudaMalloc(&h->dPixelCache, static_cast<size_t>(h->width) * h->height * atxk::kPrologueStride * sizeof(float4)));
+        p.pixelCache = h->dPixelCache;
+        if (p.maxBounces >= 1)
+            h->launches++; // pixel_prologue_kernel
+    }
     ATX_CUDA(cudaMemsetAsync(h->dPool, 0, sizeof(uint32_t), h->stream));
     ATX_CUDA(atx_launch::render_mega(p, h->megaKind, h->smCount, h->stream));
     h->launches++;

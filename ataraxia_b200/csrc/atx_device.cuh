@@ -62,6 +62,9 @@ struct RenderParams
     uint32_t tileStride, tileOffset, nTiles;
     uint32_t nPush;
     float4* push[7];
+    // per-pixel constants of the launch for the warp-queue form with at most one light (pixel_prologue_kernel):
+    // kPrologueStride float4 per pixel
+    float4* pixelCache;
     const float4* spheres;    // (-cx, -cy, -cz, r): the exact tests, hit records
     const float4* sphFilter;  // (-cx, -cy, -cz, |c|^2 - r^2 - margin): the packed line filter (filter_sphere)
     const int32_t* sphMat;
@@ -74,6 +77,12 @@ struct RenderParams
 };
 
 struct V3 { float x, y, z; };
+
+// pixelCache record (6 float4 per pixel, written by pixel_prologue_kernel, read once by the lane that claims the pixel):
+//   [0] tPrimary, cPrimary (int bits; < 0: the primary ray misses everything), pr0, ggxT0
+//   [1] c0.rgb (color after the frame-independent first bounce), raysPerStart (uint bits) | ggx0 << 8
+//   [2] o0.xyz (origin of every frame's bounce ray), tq0.x      [3] N0.xyz, tq0.y      [4] T0.xyz, tq0.z      [5] B0.xyz, -
+constexpr uint32_t kPrologueStride = 6;
 
 // ---------------------------------------------------------------------------
 // Primary ray, Camera::UpdateRayDirection (Camera.cpp:161-195) — host IEEE

@@ -649,6 +649,86 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 // Same path_* code between traces as every other form, same frame order of the sums: the
 // results are bit-identical.
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Per-pixel prologue of the warp-queue form with at most one light, as its own kernel.
+//
+// What every frame of a pixel shares there - primary ray, its hit, and the whole first bounce up to the roulette
+// (hit record, emission, shadow ray, Cook-Torrance, the roulette probability and tangent frame of the first
+// path_bounce: see megakernel_ww) - was computed by the lane that claimed the pixel. Claims come a few lanes at a
+// time (lanes finish their pixels at different moments), so those ~700 instructions ran ~3 lanes wide: 2 % of a
+// 1024-frame launch of config 2, but 16 % of a 128-frame one (one rank's share of an 8-GPU split: 3.37 ms where
+// 2.83 would be an eighth of the full render). Here one thread per pixel of the launch's pool computes them 32 lanes
+// wide and stores 96 B per pixel; the claiming lane loads them. Same functions on the same inputs: same bits.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams p)
+{
+    extern __shared__ float4 smem[];
+    float4* sphS = smem;
+    stage_spheres(sphS, p.spheres, p.nSpheres);
+    __syncthreads();
+    uint32_t traced = 0;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < p.poolSize; id += gridDim.x * blockDim.x)
+    {
+        uint32_t x, y;
+        if (!pool_pixel(p, id, x, y))
+            continue;
+        const uint32_t pixel = x + y * p.width;
+        const V3 d0 = primary_direction(p.cam, x, y, p.width, p.height);
+        PathState s;
+        path_begin(s, p.cam.pos, d0, pixel, p.firstFrame);
+        float tPrimary = 3.402823466e+38f;
+        int cPrimary = -1;
+        {
+            const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+            trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tPrimary, cPrimary);
+            traced++;
+        }
+        float4* c = p.pixelCache + static_cast<size_t>(pixel) * kPrologueStride;
+        if (cPrimary < 0)
+        {
+            c[0] = make_float4(tPrimary, __int_as_float(cPrimary), 0.0f, 0.0f);
+            continue;
+        }
+        uint32_t raysPerStart = 1u;
+        if (path_hit(p, s, sphS[cPrimary], cPrimary, tPrimary))
+        {
+            float tmin = 3.402823466e+38f;
+            int closest = -1;
+            const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
+            trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+            traced++;
+            path_shadow(p, s, closest, tmin);
+            raysPerStart = 2u;
+        }
+        // the same instructions path_bounce runs, on the values every frame would feed it
+        const float4 m0 = __ldg(p.mats + kMatStride * s.matIndex + 0);
+        const float4 m1 = __ldg(p.mats + kMatStride * s.matIndex + 1);
+        const float ax = fmul(1.0f, m0.x), ay = fmul(1.0f, m0.y), az = fmul(1.0f, m0.z);
+        const float len = fsqrt_approx(fdot3(ax, ay, az, ax, ay, az));
+        const float pr0 = fmax_(fmin_(len, 1.0f), 0.1f);
+        const bool ggx0 = m1.w > 0.0f;
+        const float ggxT0 = ggx0 ? __ldg(p.mats + kMatStride * s.matIndex + 5).x : 0.0f;
+        V3 T0, B0;
+        tangent_frame(s.N, T0, B0);
+        c[0] = make_float4(tPrimary, __int_as_float(cPrimary), pr0, ggxT0);
+        c[1] = make_float4(s.cr, s.cg, s.cb, __uint_as_float(raysPerStart | (ggx0 ? 0x100u : 0u)));
+        c[2] = make_float4(s.ox, s.oy, s.oz, fdiv_approx(ax, pr0));
+        c[3] = make_float4(s.N.x, s.N.y, s.N.z, fdiv_approx(ay, pr0));
+        c[4] = make_float4(T0.x, T0.y, T0.z, fdiv_approx(az, pr0));
+        c[5] = make_float4(B0.x, B0.y, B0.z, 0.0f);
+    }
+    // rays whose sphere loop ran (the roofline's count); the reference-equivalent count is kept by the render kernel
+    if (p.counters)
+    {
+        unsigned long long t = traced;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31u) == 0)
+            atomicAdd(p.counters + 2, t);
+    }
+}
+
 #ifndef ATX_RING
 #define ATX_RING 16
 #endif
@@ -761,6 +841,36 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             accumulate_black(acc, p.nFrames);
             store = true;
         }
+        else if (kFixedLight)
+        {
+            // one light (or none): primary hit and the frame-independent first bounce were computed for every pixel of the
+            // launch by pixel_prologue_kernel, 32 lanes wide; a claim (a few lanes at a time) only loads them
+            const float4* c = p.pixelCache + static_cast<size_t>(pixel) * kPrologueStride;
+            const float4 q0 = c[0];
+            cPrimary = __float_as_int(q0.y);
+            if (cPrimary < 0)
+            {
+                accumulate_sky(p, acc, p.nFrames);
+                rays += p.nFrames;
+                store = true;
+            }
+            else
+            {
+                const float4 q1 = c[1], q2 = c[2], q3 = c[3], q4 = c[4], q5 = c[5];
+                tPrimary = q0.x; pr0 = q0.z; ggxT0 = q0.w;
+                c0r = q1.x; c0g = q1.y; c0b = q1.z;
+                const uint32_t flags = __float_as_uint(q1.w);
+                raysPerStart = flags & 0xffu;
+                ggx0 = (flags >> 8) != 0u;
+                o0x = q2.x; o0y = q2.y; o0z = q2.z; tq0x = q2.w;
+                N0 = { q3.x, q3.y, q3.z }; tq0y = q3.w;
+                T0 = { q4.x, q4.y, q4.z }; tq0z = q4.w;
+                B0 = { q5.x, q5.y, q5.z };
+                live = true;
+                j = 0u;
+                head = 0u;
+            }
+        }
         else
         {
             // the pixel's primary ray and its hit: the same for every frame (Camera.cpp:176-187)
@@ -780,31 +890,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 j = 0u;
                 head = 0u;
                 raysPerStart = 1u;
-                if (kFixedLight)
-                {
-                    // one light (or none): the first bounce up to the roulette is frame-independent
-                    // (see megakernel_ww); run it once and keep what every frame starts from
-                    if (path_hit(p, s, sphS[cPrimary], cPrimary, tPrimary))
-                    {
-                        float tmin;
-                        int closest;
-                        trace(s, tmin, closest);
-                        path_shadow(p, s, closest, tmin);
-                        raysPerStart = 2u;
-                    }
-                    c0r = s.cr; c0g = s.cg; c0b = s.cb;
-                    o0x = s.ox; o0y = s.oy; o0z = s.oz;
-                    N0 = s.N;
-                    const float4 m0 = __ldg(p.mats + kMatStride * s.matIndex + 0);
-                    const float4 m1 = __ldg(p.mats + kMatStride * s.matIndex + 1);
-                    const float ax = fmul(1.0f, m0.x), ay = fmul(1.0f, m0.y), az = fmul(1.0f, m0.z);
-                    const float len = fsqrt_approx(fdot3(ax, ay, az, ax, ay, az));
-                    pr0 = fmax_(fmin_(len, 1.0f), 0.1f);
-                    tq0x = fdiv_approx(ax, pr0); tq0y = fdiv_approx(ay, pr0); tq0z = fdiv_approx(az, pr0);
-                    ggx0 = m1.w > 0.0f;
-                    ggxT0 = ggx0 ? __ldg(p.mats + kMatStride * s.matIndex + 5).x : 0.0f;
-                    tangent_frame(N0, T0, B0);
-                }
             }
         }
         if (store)
@@ -1663,6 +1748,9 @@ cudaError_t configure()
     e = cudaFuncSetAttribute(megakernel_wq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
+    e = cudaFuncSetAttribute(pixel_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    if (e != cudaSuccess)
+        return e;
     e = cudaFuncSetAttribute(megakernel_wq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
@@ -1690,7 +1778,18 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
         const uint32_t tiles = p.poolSize / 32u;
         const uint32_t grid = max(1u, min(static_cast<uint32_t>(smCount * max(perSm, 1)), (tiles + kWqWarps - 1u) / kWqWarps));
         if (p.nLights <= 1u)
+        {
+            if (!p.pixelCache)
+                return cudaErrorInvalidValue;
+            if (p.maxBounces >= 1)
+            {
+                // per-pixel constants of the launch, one thread per pixel of the pool (4 resident CTAs of 256 per SM is plenty)
+                const size_t psm = sizeof(float4) * ((static_cast<size_t>(p.nSpheres) + 7u) & ~size_t(7));
+                const uint32_t pgrid = max(1u, min(static_cast<uint32_t>(smCount) * 4u, (p.poolSize + 255u) / 256u));
+                pixel_prologue_kernel<<<pgrid, 256, psm, s>>>(p);
+            }
             megakernel_wq<true><<<grid, kWqWarps * 32, wq, s>>>(p);
+        }
         else
             megakernel_wq<false><<<grid, kWqWarps * 32, wq, s>>>(p);
 #ifdef ATX_WQ_STATS

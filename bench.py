@@ -514,8 +514,12 @@ def main():
             verified["reduced_vs_sequential_max_rel"] = float(err.max())
             if args.split == "tiles":   # every pixel summed on one GPU in frame order: the single-GPU bits
                 verified["tiles_bit_identical_to_sequential"] = bool((acc.view(np.uint32) == seq.view(np.uint32)).all())
-            else:                       # N partial sums added in rank order: float reassociation only
-                verified["reduced_vs_sequential"] = bool(err.max() <= 2e-6 * total_spp ** 0.5 + 2e-6)
+            else:
+                # N partial sums added in rank order against one sequential sum: float reassociation only. Both are within
+                # (n - 1) u of the exact sum of n non-negative samples (u = 2^-24), so they differ by at most 2 n u relative
+                # (8 ranks x 1024 spp measured: 2.1e-4 against the bound 9.8e-4); a missing or doubled frame shows in sample_counts
+                verified["reduced_vs_sequential_bound"] = 2.0 * total_spp * 2.0 ** -24 + 2e-6
+                verified["reduced_vs_sequential"] = bool(err.max() <= verified["reduced_vs_sequential_bound"])
         ok = torch.tensor([0.0 if verified["sample_counts"] else 1.0], device=f"cuda:{local_rank}")
         dist.all_reduce(ok, op=dist.ReduceOp.MAX)
         verified["sample_counts"] = float(ok.item()) == 0.0

@@ -745,4 +745,21 @@ def test_error_behaviour(atx):
         atx.Renderer(9999)                                          # bad device ordinal
     with pytest.raises(atx.AtxError):
         r.allreduceAccum()                                          # no communicator
-    r.close()
+    # a resize that cannot be satisfied (640 GB of accumulation) fails cleanly and leaves the old image in place
+    scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
+    cam = atx.Camera(scene.camera.getFov(), 0.1, 100.0, scene.camera.getPosition(), scene.camera.getDirection())
+    cam.Resize(16, 16)
+    r.setSettings(atx.Settings(True, True, 4))
+    r.Render(cam, scene, frames=3)
+    before = r.getAccumulation()
+    with pytest.raises(atx.AtxError, match="kept"):
+        check = __import__("ataraxia_b200._capi", fromlist=["check"])
+        check.check(check.lib().atx_resize(r._h, 200000, 200000))
+    assert (bits(r.getAccumulation()) == bits(before)).all() and r.frameIndex() == 4
+    r.Render(cam, scene, frames=2)
+    r2 = atx.Renderer(0); r2.setSettings(atx.Settings(True, True, 4)); r2.onResize(16, 16)
+    r2.Render(cam, scene, frames=5)
+    assert (bits(r.getAccumulation()) == bits(r2.getAccumulation())).all()
+    with pytest.raises(atx.AtxError, match="materials"):
+        r2.uploadArrays(atx.pack_spheres([atx.Sphere((0.0, 0.0, 0.0), 1.0, 0)]), atx.pack_materials([]), atx.pack_lights([]))
+    r.close(); r2.close()
