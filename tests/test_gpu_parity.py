@@ -472,6 +472,30 @@ def test_config5_geometry_8k(atx):
     r.close()
 
 
+def _dup_scene(atx, n, dup, seed):
+    """n random spheres + a ground sphere, then `dup` exact geometric copies of the first spheres appended with OTHER materials:
+    every hit on a copied sphere is an exact tie in t between two indices, which the reference resolves to the lower one
+    (strict '<' in an ascending loop, Renderer.cu:256-276)."""
+    scene = atx.synthetic.make_scene(n, 3, (-20.0, 0.3, -20.0), (20.0, 8.0, 20.0), 0.3, 0.9, (0.0, 9.0, 38.0), (0.0, -0.15, -1.0), seed=seed)
+    base = scene.rootNode.getSpheres()
+    for i in range(dup):
+        s = base[i]
+        scene.rootNode.addSphere(atx.Sphere(tuple(s.center), float(s.radius), (int(s.id) + 7) % len(scene.materials)))
+    return scene
+
+
+def test_exact_ties_go_to_the_lowest_index_like_the_reference(atx, tmp_path):
+    """150 exact geometric copies of spheres with other materials: every hit on a copied sphere is an exact tie in t between
+    two indices. The reference's ascending loop with a strict '<' keeps the lower index (Renderer.cu:256-276); the packed forms
+    replay candidates in ascending index, so they must agree bit for bit - on the hit ids and on the radiance that follows
+    from the chosen material. 850 spheres: 27 filter blocks, the last one partial."""
+    scene = _dup_scene(atx, 700, 150, 3)
+    p = tmp_path / "dup.json"
+    atx.Utils.exportScene(scene, str(p))
+    _live_compare(atx, p, 160, 90, 6, True, 5, kind=atx.MEGA_PAIR, expect_kind=atx.MEGA_PAIR)
+    _live_compare(atx, p, 160, 90, 6, True, 5, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
+
+
 def test_tile_shares_cover_the_image_bit_identically(atx):
     """Image-tile split on one GPU (the multi-GPU form pushes the same shares over NVLink, tests/mgpu_worker.py): the
     shares 0..R-1 of a render, launched one after the other into the same buffer, are the one-launch image bit for bit;
