@@ -494,6 +494,15 @@ def test_exact_ties_go_to_the_lowest_index_like_the_reference(atx, tmp_path):
     atx.Utils.exportScene(scene, str(p))
     _live_compare(atx, p, 160, 90, 6, True, 5, kind=atx.MEGA_PAIR, expect_kind=atx.MEGA_PAIR)
     _live_compare(atx, p, 160, 90, 6, True, 5, kind=atx.MEGA_PAIR_LOCKSTEP, expect_kind=atx.MEGA_PAIR_LOCKSTEP, one_launch=True)
+    # the same on a small scene (scalar trace of the while-while and warp-queue forms): 7 spheres + 4 copies, one light
+    small = atx.synthetic.small(7, 1, seed=12)
+    base = small.rootNode.getSpheres()
+    for i in range(4):
+        small.rootNode.addSphere(atx.Sphere(tuple(base[i].center), float(base[i].radius), (int(base[i].id) + 5) % len(small.materials)))
+    p2 = tmp_path / "dup_small.json"
+    atx.Utils.exportScene(small, str(p2))
+    _live_compare(atx, p2, 160, 90, 8, False, 12, expect_kind=atx.MEGA_WARP_QUEUE)
+    _live_compare(atx, p2, 160, 90, 8, False, 2, expect_kind=atx.MEGA_WHILE_WHILE)
 
 
 def test_tile_shares_cover_the_image_bit_identically(atx):
