@@ -47,7 +47,9 @@ def main():
                       "issue, not by the sphere loop."}
     traffic = {"_note": f"dram__bytes_read.sum + dram__bytes_write.sum of ONE megakernel launch, from the {tag} ncu --set full captures. c2: 1920x1080 "
                         "x 256 spp launch of megakernel_wq, accumulation written once (33.2 MB algorithmic) and still resident in the 126 MB L2 when "
-                        "the kernel ends; c3/c4: 3840x2160 launches of the packed forms (132.7 MB algorithmic write), partly evicted to HBM."}
+                        "the kernel ends, plus since r02k the 96 B per pixel of launch constants the claiming lanes read (199 MB at 1080p, written by "
+                        "pixel_prologue_kernel just before: the price of running the per-pixel prologue 32 lanes wide instead of 3); c3/c4: 3840x2160 "
+                        "launches of the packed forms (132.7 MB algorithmic write), partly evicted to HBM."}
     for spec in sys.argv[2:]:
         name, rep = spec.split("=")
         r = raw(rep)
