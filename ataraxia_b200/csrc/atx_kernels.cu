@@ -1,17 +1,20 @@
 // atx_kernels.cu — hand-written sm_100a kernels of the path-tracing hot path.
 //
-//   pack_scene_kernel   AoS reference records -> SoA float4 rows (once per upload)
-//   megakernel          kernelRender + perPixel (Renderer.cu:150-170, :287-387):
-//                       one thread per pixel runs ALL requested frames of that pixel
-//                       in one flattened trace loop with path regeneration, sums the
-//                       samples in registers in the reference's order and touches the
-//                       float4 accumulation buffer once (16 B read + 16 B write)
-//   primary_hit_kernel  parity/debug: closest sphere per primary ray
-//   ray_dir_kernel      parity/debug: the primary ray table
-//   resolve_rgba_kernel display pack of the accumulation buffer
+//   pack_scene_kernel      AoS reference records -> SoA float4 rows (once per upload), incl. the line filter's records
+//   megakernel_*           kernelRender + perPixel (Renderer.cu:150-170, :287-387) as persistent kernels over a pixel
+//                          pool: a lane (or a path slot) runs ALL requested frames of a pixel, sums the samples in the
+//                          reference's frame order and touches the float4 accumulation buffer once (16 B read + 16 B write)
+//       _ww                  while-while form: small scenes, few frames per launch or several lights
+//       _wq                  warp-queue form: small scenes, hits queued per warp and bounced 32 at a time
+//       _pair                two path slots per thread, packed f32x2 line filter + exact replay, slots free-running
+//       _pair_ls             the same trace with all slots of a CTA in lockstep (closest-hit trace, shadow trace)
+//   pixel_prologue_kernel  per-pixel launch constants of the warp-queue form, 32 lanes wide
+//   primary_hit_kernel     parity/debug: closest sphere per primary ray
+//   ray_dir_kernel         parity/debug: the primary ray table
+//   resolve_rgba_kernel    display pack of the accumulation buffer
 //
-// No tensor cores: no stage of this path is a dense contraction. The bound is the
-// FP32 FMA pipe (sphere loop) and MUFU (shading); see DESIGN.md §5.
+// No tensor cores: no stage of this path is a dense contraction. The bound is FP32 issue (sphere loop) and
+// instruction issue at large (shading); see DESIGN.md sections 3 and 5.
 #include "atx_device.cuh"
 #include "atx_kernels.h"
 #include <cstdio>
