@@ -183,6 +183,35 @@ ATX_DEV void exact_test(const float4 sp, int index, float ox, float oy, float oz
     exact_tail(hb, cc, index, k, tmin, closest);
 }
 
+// The reference's literal sequence for one sphere WITHOUT its branch (Renderer.cu:263-278): where the reference skips
+// (disc < 0) sqrt.approx yields NaN, t0, t1 and their minimum are NaN, and "t > 0 && t < tmin" is false - the same
+// outcome as the skip; a NaN or -0 disc takes the same instructions in both. 25 instructions per sphere at full
+// width and no BSSY/BRA/BSYNC: with a handful of spheres that is fewer issue slots than a filter in front plus a hit
+// branch that runs a few lanes wide almost every time (3-sphere scene: 23 + 18 per sphere).
+ATX_DEV void flat_tail(float hb, float cc, int index, const RayConst& k, float& tmin, int& closest)
+{
+    const float b = fadd(hb, hb);
+    const float disc = ffma(b, b, fneg(fmul(k.a4, cc)));
+    const float sq = fsqrt_approx(disc);
+    const float t0 = fdiv_approx(fsub(fneg(b), sq), k.a2);
+    const float t1 = fdiv_approx(fsub(sq, b), k.a2);
+    const float t = t0 < t1 ? t0 : t1;
+    const bool hit = t > 0.0f && t < tmin;
+    tmin = hit ? t : tmin;
+    closest = hit ? index : closest;
+}
+
+ATX_DEV void exact_flat(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
+                        const RayConst& k, float& tmin, int& closest)
+{
+    const float ocx = fadd(ox, sp.x);
+    const float ocy = fadd(oy, sp.y);
+    const float ocz = fadd(oz, sp.z);
+    const float hb = fdot3(ocx, ocy, ocz, dx, dy, dz);
+    const float cc = ffma(fneg(sp.w), sp.w, fdot3(ocx, ocy, ocz, ocx, ocy, ocz));
+    flat_tail(hb, cc, index, k, tmin, closest);
+}
+
 // scalar test with the cheap line filter in front (small scenes, debug kernels)
 ATX_DEV void intersect_sphere(const float4 sp, int index, float ox, float oy, float oz, float dx, float dy, float dz,
                               const RayConst& k, float& tmin, int& closest)

@@ -131,13 +131,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // scalar: one ray against spheres [0, count) resident at `sph`; indices offset by base
+// kCount > 0: the scene has exactly kCount spheres (compile-time: straight-line code, the tests of one ray interleave)
+template <bool kFlat = false, int kCount = 0>
 __device__ __forceinline__ void trace_range(const float4* sph, uint32_t count, uint32_t base,
                                             float ox, float oy, float oz, float dx, float dy, float dz,
                                             const RayConst& k, float& tmin, int& closest)
 {
+    if (kCount > 0)
+    {
+#pragma unroll
+        for (int i = 0; i < kCount; i++)
+        {
+            if (kFlat)
+                exact_flat(sph[i], static_cast<int>(base) + i, ox, oy, oz, dx, dy, dz, k, tmin, closest);
+            else
+                intersect_sphere(sph[i], static_cast<int>(base) + i, ox, oy, oz, dx, dy, dz, k, tmin, closest);
+        }
+        return;
+    }
 #pragma unroll 4
     for (uint32_t i = 0; i < count; i++)
-        intersect_sphere(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
+    {
+        if (kFlat)
+            exact_flat(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
+        else
+            intersect_sphere(sph[i], static_cast<int>(base + i), ox, oy, oz, dx, dy, dz, k, tmin, closest);
+    }
 }
 
 // packed: the two rays of a thread against the filter records of spheres [0, count) resident at `sph`
@@ -750,6 +769,15 @@ __global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams 
 #ifndef ATX_WQ_CONSUME
 #define ATX_WQ_CONSUME 3u // completed ring slots are added to the sums every (mask + 1)th pass (measured at one frame per pass: every pass 24.4 ms, 2nd 24.1, 4th 23.9, 8th 23.8)
 #endif
+#ifndef ATX_WQ_FLAT
+#define ATX_WQ_FLAT 1 // sphere tests of the warp-queue form: 1 = the reference's sequence branch-free (exact_flat), 0 = line filter + hit branch
+#endif
+#ifndef ATX_WQ_HOIST
+#define ATX_WQ_HOIST 1 // one light, compile-time sphere count: origin-only part of the G-phase sphere tests kept per pixel
+#endif
+#ifndef ATX_WQ_STATIC
+#define ATX_WQ_STATIC 4 // scenes of up to this many spheres get a warp-queue kernel with the count compiled in (0: none)
+#endif
 #ifndef ATX_WQ_BFULL
 #define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
 #endif
@@ -767,9 +795,15 @@ __device__ unsigned long long g_wqStats[8];
 #define WQ_STAT(i, v) do { } while (0)
 #endif
 
-template <bool kFixedLight>
+template <bool kFixedLight, int kN>
 __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(const RenderParams p)
 {
+    // kN > 0: the scene has exactly kN spheres. The sphere tests are then straight-line code, and with one light the
+    // part of a test that depends on the ray ORIGIN only is a per-pixel constant of the launch as well: every frame's
+    // bounce ray leaves the cached first hit o0, so oc = o0 - c and cc = |oc|^2 - r^2 are formed once per claim
+    // (same instructions on the same inputs as Renderer.cu:263-266) and a test in G is 3 + 15 instructions
+    constexpr bool kHoist = kFixedLight && kN > 0 && ATX_WQ_HOIST != 0;
+    constexpr int kH = kHoist ? kN : 1;
     extern __shared__ float4 smem[];
     float4* sphS = smem;
     constexpr unsigned kFull = 0xffffffffu;
@@ -793,7 +827,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
         tmin = 3.402823466e+38f; // FLT_MAX
         closest = -1;
         const RayConst rk = ray_constants(dx, dy, dz);
-        trace_range(sphS, p.nSpheres, 0u, ox, oy, oz, dx, dy, dz, rk, tmin, closest);
+        trace_range<ATX_WQ_FLAT != 0, kN>(sphS, p.nSpheres, 0u, ox, oy, oz, dx, dy, dz, rk, tmin, closest);
         traced++;
     };
     auto trace = [&](const PathState& s, float& tmin, int& closest) { trace_ray(s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, tmin, closest); };
@@ -820,6 +854,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     V3 N0 = { 0.0f, 0.0f, 0.0f }, T0 = { 0.0f, 0.0f, 0.0f }, B0 = { 0.0f, 0.0f, 0.0f };
     float pr0 = 0.0f, tq0x = 0.0f, tq0y = 0.0f, tq0z = 0.0f, ggxT0 = 0.0f;
     bool ggx0 = false;
+    float hocx[kH] = {}, hocy[kH] = {}, hocz[kH] = {}, hcc[kH] = {};
     uint32_t qHead = 0u, qCount = 0u, stallDebt = 0u, pass = 0u;
     done[lane] = 0u;
     __syncwarp();
@@ -869,6 +904,18 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 N0 = { q3.x, q3.y, q3.z }; tq0y = q3.w;
                 T0 = { q4.x, q4.y, q4.z }; tq0z = q4.w;
                 B0 = { q5.x, q5.y, q5.z };
+                if (kHoist)
+                {
+#pragma unroll
+                    for (int i = 0; i < kH; i++)
+                    {
+                        const float4 sp = sphS[i];
+                        hocx[i] = fadd(o0x, sp.x);
+                        hocy[i] = fadd(o0y, sp.y);
+                        hocz[i] = fadd(o0z, sp.z);
+                        hcc[i] = ffma(fneg(sp.w), sp.w, fdot3(hocx[i], hocy[i], hocz[i], hocx[i], hocy[i], hocz[i]));
+                    }
+                }
                 live = true;
                 j = 0u;
                 head = 0u;
@@ -1068,7 +1115,18 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                         }
                         if (flying)
                         {
-                            trace_ray(o0x, o0y, o0z, nd.x, nd.y, nd.z, hitT, hitC);
+                            if (kHoist)
+                            {
+                                hitT = 3.402823466e+38f; // FLT_MAX
+                                hitC = -1;
+                                const RayConst rk = ray_constants(nd.x, nd.y, nd.z);
+#pragma unroll
+                                for (int i = 0; i < kH; i++)
+                                    flat_tail(fdot3(hocx[i], hocy[i], hocz[i], nd.x, nd.y, nd.z), hcc[i], i, rk, hitT, hitC);
+                                traced++;
+                            }
+                            else
+                                trace_ray(o0x, o0y, o0z, nd.x, nd.y, nd.z, hitT, hitC);
                             rays++;
                             hit = hitC >= 0;
                         }
@@ -1728,6 +1786,46 @@ size_t megakernel_smem_bytes(const RenderParams& p)
     return sizeof(float4) * (1 + (chunked ? 2 * pad : pad)) + sizeof(uint32_t) * cand_words(p) * threads; // +16 B: two mbarriers
 }
 
+// the warp-queue kernel of a scene: one light or several, sphere count compiled in for the smallest scenes
+typedef void (*WqKernel)(const RenderParams);
+template <bool kFixedLight>
+static WqKernel wq_kernel_by_count(uint32_t nSpheres)
+{
+    switch (nSpheres <= ATX_WQ_STATIC ? nSpheres : 0u)
+    {
+#if ATX_WQ_STATIC >= 1
+    case 1: return megakernel_wq<kFixedLight, 1>;
+#endif
+#if ATX_WQ_STATIC >= 2
+    case 2: return megakernel_wq<kFixedLight, 2>;
+#endif
+#if ATX_WQ_STATIC >= 3
+    case 3: return megakernel_wq<kFixedLight, 3>;
+#endif
+#if ATX_WQ_STATIC >= 4
+    case 4: return megakernel_wq<kFixedLight, 4>;
+#endif
+    default: return megakernel_wq<kFixedLight, 0>;
+    }
+}
+static WqKernel wq_kernel(const RenderParams& p)
+{
+    return p.nLights <= 1u ? wq_kernel_by_count<true>(p.nSpheres) : wq_kernel_by_count<false>(p.nSpheres);
+}
+static cudaError_t configure_wq()
+{
+    for (uint32_t n = 0; n <= ATX_WQ_STATIC; n++)
+    {
+        cudaError_t e = cudaFuncSetAttribute(wq_kernel_by_count<true>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (e != cudaSuccess)
+            return e;
+        e = cudaFuncSetAttribute(wq_kernel_by_count<false>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t configure()
 {
     cudaError_t e = cudaFuncSetAttribute(megakernel_ww<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
@@ -1748,13 +1846,10 @@ cudaError_t configure()
     e = cudaFuncSetAttribute(megakernel_pair_ls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
-    e = cudaFuncSetAttribute(megakernel_wq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    e = configure_wq();
     if (e != cudaSuccess)
         return e;
     e = cudaFuncSetAttribute(pixel_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
-    if (e != cudaSuccess)
-        return e;
-    e = cudaFuncSetAttribute(megakernel_wq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
     return configure_wavefront();
@@ -1772,9 +1867,8 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
         if (wq > static_cast<size_t>(kMaxSmemBytes))
             return cudaErrorInvalidValue;
         int perSm = 0;
-        cudaError_t e = p.nLights <= 1u
-                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, megakernel_wq<true>, kWqWarps * 32, wq)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, megakernel_wq<false>, kWqWarps * 32, wq);
+        const WqKernel kernel = wq_kernel(p);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWqWarps * 32, wq);
         if (e != cudaSuccess)
             return e;
         // no more CTAs than the image has 8x4 tiles per warp
@@ -1791,10 +1885,8 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
                 const uint32_t pgrid = max(1u, min(static_cast<uint32_t>(smCount) * 4u, (p.poolSize + 255u) / 256u));
                 pixel_prologue_kernel<<<pgrid, 256, psm, s>>>(p);
             }
-            megakernel_wq<true><<<grid, kWqWarps * 32, wq, s>>>(p);
         }
-        else
-            megakernel_wq<false><<<grid, kWqWarps * 32, wq, s>>>(p);
+        kernel<<<grid, kWqWarps * 32, wq, s>>>(p);
 #ifdef ATX_WQ_STATS
         {
             unsigned long long st[8], zero[8] = {};
