@@ -183,19 +183,23 @@ ATX_DEV void exact_test(const float4 sp, int index, float ox, float oy, float oz
     exact_tail(hb, cc, index, k, tmin, closest);
 }
 
-// The reference's literal sequence for one sphere WITHOUT its branch (Renderer.cu:263-278): where the reference skips
-// (disc < 0) sqrt.approx yields NaN, t0, t1 and their minimum are NaN, and "t > 0 && t < tmin" is false - the same
-// outcome as the skip; a NaN or -0 disc takes the same instructions in both. 25 instructions per sphere at full
-// width and no BSSY/BRA/BSYNC: with a handful of spheres that is fewer issue slots than a filter in front plus a hit
-// branch that runs a few lanes wide almost every time (3-sphere scene: 23 + 18 per sphere).
+// The reference's sequence for one sphere WITHOUT its branches (Renderer.cu:263-278), 11 instructions behind hb and cc:
+//  * "if (disc < 0) continue" is dropped: sqrt.approx of a negative disc is NaN, so is t, and "t > 0 && t < tmin" is
+//    false - the outcome of the skip; a NaN or -0 disc takes the same instructions in both;
+//  * t = min(t0, t1) is t0: with sq = sqrt.approx(disc) >= 0 (or -0) the exact values satisfy -b - sq <= sq - b,
+//    rounding to nearest is monotonic, and so is the multiplication by rcp.approx(a2) >= 0 (a2 = 2 dot(d,d) >= +0, so
+//    the reciprocal is never negative): t0 <= t1 whenever both are numbers, and where they are equal they are the same
+//    number (a zero of either sign fails "t > 0"). t0 is NaN with t1 a number only for b = -inf (t1 = +inf, no hit:
+//    "t < tmin") or a2 in {0, inf} with t1 in {NaN, 0, inf} (no hit) - and a NaN t0 reports no hit as well. So
+//    (hit, t) are those of "t0 < t1 ? t0 : t1" for every input, and t1 never needs to exist.
+// With a handful of spheres this is fewer issue slots than a filter in front plus a hit branch that runs a few lanes
+// wide almost every time (3-sphere scene: 23 + 18 instructions per sphere), and the tests of one ray interleave.
 ATX_DEV void flat_tail(float hb, float cc, int index, const RayConst& k, float& tmin, int& closest)
 {
     const float b = fadd(hb, hb);
     const float disc = ffma(b, b, fneg(fmul(k.a4, cc)));
     const float sq = fsqrt_approx(disc);
-    const float t0 = fdiv_approx(fsub(fneg(b), sq), k.a2);
-    const float t1 = fdiv_approx(fsub(sq, b), k.a2);
-    const float t = t0 < t1 ? t0 : t1;
+    const float t = fdiv_approx(fsub(fneg(b), sq), k.a2);
     const bool hit = t > 0.0f && t < tmin;
     tmin = hit ? t : tmin;
     closest = hit ? index : closest;
