@@ -395,7 +395,14 @@ __device__ __forceinline__ void accumulate_sky(const RenderParams& p, float4& ac
 // bit-identical to sequential reference frames, and the accumulation buffer is touched
 // once: one 16 B read + one 16 B write per pixel per launch.
 // ---------------------------------------------------------------------------
-template <bool kFixedLight>
+#ifndef ATX_WW_FLAT
+#define ATX_WW_FLAT 1 // sphere tests of the while-while form: 1 = branch-free (exact_flat), 0 = line filter + hit branch
+#endif
+#ifndef ATX_SMALL_STATIC
+#define ATX_SMALL_STATIC 4 // scenes of up to this many spheres get small-scene kernels with the count compiled in (0: none)
+#endif
+// kN > 0: the scene has exactly kN spheres (straight-line sphere tests); 0: any count up to kWhileWhileMaxSpheres
+template <bool kFixedLight, int kN>
 __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 {
     extern __shared__ float4 smem[];
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
         tmin = 3.402823466e+38f; // FLT_MAX
         closest = -1;
         const RayConst rk = ray_constants(s.dx, s.dy, s.dz);
-        trace_range(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
+        trace_range<ATX_WW_FLAT != 0, kN>(sphS, p.nSpheres, 0u, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, rk, tmin, closest);
         traced++;
     };
     // the pixel is complete: st.global.v4.f32 of the running sum (+ the display pack)
@@ -774,9 +781,6 @@ __global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams 
 #endif
 #ifndef ATX_WQ_HOIST
 #define ATX_WQ_HOIST 1 // one light, compile-time sphere count: origin-only part of the G-phase sphere tests kept per pixel
-#endif
-#ifndef ATX_WQ_STATIC
-#define ATX_WQ_STATIC 4 // scenes of up to this many spheres get a warp-queue kernel with the count compiled in (0: none)
 #endif
 #ifndef ATX_WQ_BFULL
 #define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
@@ -1791,18 +1795,18 @@ typedef void (*WqKernel)(const RenderParams);
 template <bool kFixedLight>
 static WqKernel wq_kernel_by_count(uint32_t nSpheres)
 {
-    switch (nSpheres <= ATX_WQ_STATIC ? nSpheres : 0u)
+    switch (nSpheres <= ATX_SMALL_STATIC ? nSpheres : 0u)
     {
-#if ATX_WQ_STATIC >= 1
+#if ATX_SMALL_STATIC >= 1
     case 1: return megakernel_wq<kFixedLight, 1>;
 #endif
-#if ATX_WQ_STATIC >= 2
+#if ATX_SMALL_STATIC >= 2
     case 2: return megakernel_wq<kFixedLight, 2>;
 #endif
-#if ATX_WQ_STATIC >= 3
+#if ATX_SMALL_STATIC >= 3
     case 3: return megakernel_wq<kFixedLight, 3>;
 #endif
-#if ATX_WQ_STATIC >= 4
+#if ATX_SMALL_STATIC >= 4
     case 4: return megakernel_wq<kFixedLight, 4>;
 #endif
     default: return megakernel_wq<kFixedLight, 0>;
@@ -1812,14 +1816,44 @@ static WqKernel wq_kernel(const RenderParams& p)
 {
     return p.nLights <= 1u ? wq_kernel_by_count<true>(p.nSpheres) : wq_kernel_by_count<false>(p.nSpheres);
 }
+template <bool kFixedLight>
+static WqKernel ww_kernel_by_count(uint32_t nSpheres)
+{
+    switch (nSpheres <= ATX_SMALL_STATIC ? nSpheres : 0u)
+    {
+#if ATX_SMALL_STATIC >= 1
+    case 1: return megakernel_ww<kFixedLight, 1>;
+#endif
+#if ATX_SMALL_STATIC >= 2
+    case 2: return megakernel_ww<kFixedLight, 2>;
+#endif
+#if ATX_SMALL_STATIC >= 3
+    case 3: return megakernel_ww<kFixedLight, 3>;
+#endif
+#if ATX_SMALL_STATIC >= 4
+    case 4: return megakernel_ww<kFixedLight, 4>;
+#endif
+    default: return megakernel_ww<kFixedLight, 0>;
+    }
+}
+static WqKernel ww_kernel(const RenderParams& p)
+{
+    return p.nLights <= 1u ? ww_kernel_by_count<true>(p.nSpheres) : ww_kernel_by_count<false>(p.nSpheres);
+}
 static cudaError_t configure_wq()
 {
-    for (uint32_t n = 0; n <= ATX_WQ_STATIC; n++)
+    for (uint32_t n = 0; n <= ATX_SMALL_STATIC; n++)
     {
         cudaError_t e = cudaFuncSetAttribute(wq_kernel_by_count<true>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
         if (e != cudaSuccess)
             return e;
         e = cudaFuncSetAttribute(wq_kernel_by_count<false>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (e != cudaSuccess)
+            return e;
+        e = cudaFuncSetAttribute(ww_kernel_by_count<true>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+        if (e != cudaSuccess)
+            return e;
+        e = cudaFuncSetAttribute(ww_kernel_by_count<false>(n), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
         if (e != cudaSuccess)
             return e;
     }
@@ -1828,13 +1862,7 @@ static cudaError_t configure_wq()
 
 cudaError_t configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(megakernel_ww<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
-    if (e != cudaSuccess)
-        return e;
-    e = cudaFuncSetAttribute(megakernel_ww<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
-    if (e != cudaSuccess)
-        return e;
-    e = cudaFuncSetAttribute(megakernel_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(megakernel_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess)
         return e;
     e = cudaFuncSetAttribute(megakernel_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
@@ -1903,10 +1931,7 @@ cudaError_t render_mega(const RenderParams& p, int kind, int smCount, cudaStream
     if (mega_kind(p, kind) == kMegaWhileWhile)
     {
         const uint32_t grid = min(static_cast<uint32_t>(smCount) * 3u, byWork);
-        if (p.nLights <= 1u)
-            megakernel_ww<true><<<grid, 256, smem, s>>>(p);
-        else
-            megakernel_ww<false><<<grid, 256, smem, s>>>(p);
+        ww_kernel(p)<<<grid, 256, smem, s>>>(p);
     }
     else
     {
