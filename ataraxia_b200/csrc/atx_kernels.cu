@@ -782,6 +782,12 @@ __global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams 
 #ifndef ATX_WQ_HOIST
 #define ATX_WQ_HOIST 1 // one light, compile-time sphere count: origin-only part of the G-phase sphere tests kept per pixel
 #endif
+#ifndef ATX_WQ_GDUAL
+#define ATX_WQ_GDUAL 1 // one light: G generates frames in pairs, side by side in straight-line code
+#endif
+#ifndef ATX_WQ_GPAIRS
+#define ATX_WQ_GPAIRS 2u // pairs per pass of the warp loop (config 2: one pair 17.62 ms, two 17.29)
+#endif
 #ifndef ATX_WQ_BFULL
 #define ATX_WQ_BFULL 32u // queued hits that trigger a bounce pass with no stall debt
 #endif
@@ -1063,7 +1069,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             else if (genMask != 0u)
             {
                 // ---- G: the next frame of this lane's pixel ----
-                stallDebt += nStalled * (kFixedLight ? ATX_WQ_GREPEAT : 1u);
+                stallDebt += nStalled * (kFixedLight ? (ATX_WQ_GDUAL ? 2u * ATX_WQ_GPAIRS : ATX_WQ_GREPEAT) : 1u);
                 WQ_STAT(0, 1); WQ_STAT(1, __popc(genMask)); WQ_STAT(2, nStalled);
                 WQ_STAT(3, __popc(__ballot_sync(kFull, live && j >= p.nFrames)));
                 if (!kFixedLight)
@@ -1085,6 +1091,148 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in. The path
                     // state of this branch IS the per-pixel constants plus a seed and a direction, so it is kept in
                     // its own registers and queued from them (no copy into a PathState)
+#if ATX_WQ_GDUAL
+                    // Two frames side by side in straight-line code: the three hashes, the sampler and the sphere tests
+                    // of frame j and frame j + 1 are independent chains, so they fill each other's latencies (five warps
+                    // per scheduler do not hide a serial PCG chain on their own). A lane whose path dies at the roulette
+                    // computes the rest anyway - it would idle behind the others' branch otherwise.
+#pragma unroll
+                    for (uint32_t rep = 0u; rep < ATX_WQ_GPAIRS; rep++)
+                    {
+                        const uint32_t inFlight = j - head;
+                        const bool onA = rep == 0u ? gen : (live && j < p.nFrames && inFlight < K);
+                        bool onB = onA && j + 1u < p.nFrames && inFlight + 1u < K;
+                        const uint32_t frameA = p.firstFrame + j * p.frameStride;
+                        uint32_t seedA = pixel * frameA, seedB = pixel * (frameA + p.frameStride);
+                        const float uA = pcg_float(seedA), uB = pcg_float(seedB);
+                        float xA, yA, zA, xB, yB, zB;
+                        sample_local(ggx0, ggxT0, seedA, xA, yA, zA);
+                        sample_local(ggx0, ggxT0, seedB, xB, yB, zB);
+                        const V3 ndA = frame_combine(N0, T0, B0, xA, yA, zA);
+                        const V3 ndB = frame_combine(N0, T0, B0, xB, yB, zB);
+                        seedA += 1u; // Renderer.cu:306
+                        seedB += 1u;
+                        const bool deep = 1 < p.maxBounces;
+                        const bool flyA = onA && deep && !(uA > pr0);
+                        bool flyB = onB && deep && !(uB > pr0);
+                        float tA = 3.402823466e+38f, tB = 3.402823466e+38f; // FLT_MAX
+                        int cA = -1, cB = -1;
+                        if (kHoist)
+                        {
+                            const RayConst rkA = ray_constants(ndA.x, ndA.y, ndA.z), rkB = ray_constants(ndB.x, ndB.y, ndB.z);
+#pragma unroll
+                            for (int i = 0; i < kH; i++)
+                            {
+                                flat_tail(fdot3(hocx[i], hocy[i], hocz[i], ndA.x, ndA.y, ndA.z), hcc[i], i, rkA, tA, cA);
+                                flat_tail(fdot3(hocx[i], hocy[i], hocz[i], ndB.x, ndB.y, ndB.z), hcc[i], i, rkB, tB, cB);
+                            }
+                        }
+                        else
+                        {
+                            if (flyA)
+                                trace_ray(o0x, o0y, o0z, ndA.x, ndA.y, ndA.z, tA, cA);
+                            if (flyB)
+                                trace_ray(o0x, o0y, o0z, ndB.x, ndB.y, ndB.z, tB, cB);
+                        }
+                        const bool hitA = flyA && cA >= 0;
+                        bool hitB = flyB && cB >= 0;
+                        // Queue room. A lane's first hit always fits (at most 32 queued when a pair starts, at most 32 first
+                        // hits). A second hit that would not fit is taken back together with its frame: nothing of frame j + 1
+                        // has been recorded yet, and the next pass generates it again from the same seed.
+                        const unsigned mA = __ballot_sync(kFull, hitA), mB = __ballot_sync(kFull, hitB);
+                        const unsigned m1 = mA | mB;
+                        const uint32_t below = (1u << lane) - 1u;
+                        const uint32_t n1 = __popc(m1);
+                        if (hitA && hitB && static_cast<uint32_t>(__popc(mA & mB & below)) >= kQueueCap - qCount - n1)
+                        {
+                            if (!kHoist)
+                                traced--; // (trace_ray has counted the sphere loop of the frame that is taken back)
+                            onB = false;
+                            flyB = false;
+                            hitB = false;
+                        }
+                        const unsigned m2 = __ballot_sync(kFull, hitA && hitB);
+                        const uint32_t tagA = lane | ((j & (K - 1u)) << 8), tagB = lane | (((j + 1u) & (K - 1u)) << 8);
+                        if (onA)
+                            rays += raysPerStart + (flyA ? 1u : 0u);
+                        if (onB)
+                            rays += raysPerStart + (flyB ? 1u : 0u);
+                        if (kHoist)
+                            traced += (flyA ? 1u : 0u) + (flyB ? 1u : 0u);
+                        // samples that are complete, in frame order: the cached color (+ the sky seen by the bounce ray,
+                        // path_miss); straight to the sum when nothing older is pending
+                        if (onA && !hitA)
+                        {
+                            float cr = c0r, cg = c0g, cb = c0b;
+                            if (flyA && p.skyLight)
+                            {
+                                cr = ffma(tq0x, 0.6f, cr);
+                                cg = ffma(tq0y, 0.7f, cg);
+                                cb = ffma(tq0z, 0.9f, cb);
+                            }
+                            if (head == j)
+                            {
+                                acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
+                                acc.w = fadd(acc.w, 1.0f);
+                                head++;
+                            }
+                            else
+                                complete3(tagA, cr, cg, cb);
+                        }
+                        if (onB && !hitB)
+                        {
+                            float cr = c0r, cg = c0g, cb = c0b;
+                            if (flyB && p.skyLight)
+                            {
+                                cr = ffma(tq0x, 0.6f, cr);
+                                cg = ffma(tq0y, 0.7f, cg);
+                                cb = ffma(tq0z, 0.9f, cb);
+                            }
+                            if (head == j + 1u)
+                            {
+                                acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
+                                acc.w = fadd(acc.w, 1.0f);
+                                head++;
+                            }
+                            else
+                                complete3(tagB, cr, cg, cb);
+                        }
+                        j += (onA ? 1u : 0u) + (onB ? 1u : 0u);
+                        if (hitA || hitB)
+                        {
+                            const uint32_t e = (qHead + qCount + __popc(m1 & below)) & (kQueueCap - 1u);
+                            qf[0u * kQueueCap + e] = o0x; qf[1u * kQueueCap + e] = o0y; qf[2u * kQueueCap + e] = o0z;
+                            qf[3u * kQueueCap + e] = hitA ? ndA.x : ndB.x; qf[4u * kQueueCap + e] = hitA ? ndA.y : ndB.y; qf[5u * kQueueCap + e] = hitA ? ndA.z : ndB.z;
+                            qf[6u * kQueueCap + e] = c0r; qf[7u * kQueueCap + e] = c0g; qf[8u * kQueueCap + e] = c0b;
+                            qf[9u * kQueueCap + e] = tq0x; qf[10u * kQueueCap + e] = tq0y; qf[11u * kQueueCap + e] = tq0z;
+                            q[12u * kQueueCap + e] = hitA ? seedA : seedB;
+                            q[13u * kQueueCap + e] = 1u; // bounce
+                            qf[14u * kQueueCap + e] = hitA ? tA : tB;
+                            q[15u * kQueueCap + e] = static_cast<uint32_t>(hitA ? cA : cB);
+                            q[16u * kQueueCap + e] = hitA ? tagA : tagB;
+                        }
+                        qCount += n1;
+                        if (m2 != 0u)
+                        {
+                            if (hitA && hitB)
+                            {
+                                const uint32_t e = (qHead + qCount + __popc(m2 & below)) & (kQueueCap - 1u);
+                                qf[0u * kQueueCap + e] = o0x; qf[1u * kQueueCap + e] = o0y; qf[2u * kQueueCap + e] = o0z;
+                                qf[3u * kQueueCap + e] = ndB.x; qf[4u * kQueueCap + e] = ndB.y; qf[5u * kQueueCap + e] = ndB.z;
+                                qf[6u * kQueueCap + e] = c0r; qf[7u * kQueueCap + e] = c0g; qf[8u * kQueueCap + e] = c0b;
+                                qf[9u * kQueueCap + e] = tq0x; qf[10u * kQueueCap + e] = tq0y; qf[11u * kQueueCap + e] = tq0z;
+                                q[12u * kQueueCap + e] = seedB;
+                                q[13u * kQueueCap + e] = 1u;
+                                qf[14u * kQueueCap + e] = tB;
+                                q[15u * kQueueCap + e] = static_cast<uint32_t>(cB);
+                                q[16u * kQueueCap + e] = tagB;
+                            }
+                            qCount += __popc(m2);
+                        }
+                        if (qCount > 32u)
+                            break;
+                    }
+#else
 #if ATX_WQ_GUNROLL == 1
 #pragma unroll
 #elif ATX_WQ_GUNROLL == 2
@@ -1174,6 +1322,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     if (qCount > 32u)
                         break;
                     }
+#endif
                 }
             }
             else if (__all_sync(kFull, exhausted && !live))
