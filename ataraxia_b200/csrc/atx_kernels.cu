@@ -677,6 +677,21 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 // 32-slot ring at 12 warps per SM is slower (32.5 ms), an 8-slot ring at 24 warps equal.
 // Same path_* code between traces as every other form, same frame order of the sums: the
 // results are bit-identical.
+//
+// Round 2, 22.6 -> 17.3 ms on config 2 (all bit-identical to the reference's 1024 frames):
+//  * sphere tests as the reference's sequence without its branches and without its second root
+//    (flat_tail, atx_device.cuh), sphere count compiled in for scenes of up to 4 spheres (kN): the
+//    tests of a ray are straight-line code and interleave (-> 20.6 ms);
+//  * with one light every frame's bounce ray leaves the same cached hit, so the origin-only part
+//    of each test (oc = o0 - c, cc = |oc|^2 - r^2) is kept per pixel (kHoist, -> 19.4, 18.7 ms);
+//  * G generates frames in PAIRS, side by side in one basic block: the hashes, samplers and sphere
+//    tests of frame j and j + 1 are independent chains the scheduler interleaves, the pass overhead
+//    is paid once per four frames, and a lane's first hit of a pair costs one push (-> 17.3 ms).
+// Measured and not kept: a 32-frame window with two-bit codes for samples that end without a
+// queued hit (fewer ring stalls - 29.2 lanes generating instead of 28.3 - but every sample then
+// goes through the summing loop: 19.3 ms); the bounce pass tracing its shadow ray and its
+// continuing ray together (+0.9 ms); per-pixel constants shuffled from the owning lane instead
+// of queued (+0.2 ms); three pairs per pass, other bookkeeping periods and claim sizes (+-0.5 %).
 // ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
 // Per-pixel prologue of the warp-queue form with at most one light, as its own kernel.
@@ -767,12 +782,6 @@ __global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams 
 #ifndef ATX_WQ_BOOKKEEP
 #define ATX_WQ_BOOKKEEP 7u // retire/claim check every 8th pass of the warp loop (power of two minus one; measured: every pass 25.5 ms, 4th 24.7, 8th 24.5)
 #endif
-#ifndef ATX_WQ_GUNROLL
-#define ATX_WQ_GUNROLL 1
-#endif
-#ifndef ATX_WQ_GREPEAT
-#define ATX_WQ_GREPEAT 2u // frames a lane generates per pass of the warp loop (one light; measured: 1: 23.4 ms, 2: 22.6, 3: 23.5)
-#endif
 #ifndef ATX_WQ_CONSUME
 #define ATX_WQ_CONSUME 3u // completed ring slots are added to the sums every (mask + 1)th pass (measured at one frame per pass: every pass 24.4 ms, 2nd 24.1, 4th 23.9, 8th 23.8)
 #endif
@@ -781,9 +790,6 @@ __global__ void __launch_bounds__(256) pixel_prologue_kernel(const RenderParams 
 #endif
 #ifndef ATX_WQ_HOIST
 #define ATX_WQ_HOIST 1 // one light, compile-time sphere count: origin-only part of the G-phase sphere tests kept per pixel
-#endif
-#ifndef ATX_WQ_GDUAL
-#define ATX_WQ_GDUAL 1 // one light: G generates frames in pairs, side by side in straight-line code
 #endif
 #ifndef ATX_WQ_GPAIRS
 #define ATX_WQ_GPAIRS 2u // pairs per pass of the warp loop (config 2: one pair 17.62 ms, two 17.29)
@@ -1069,7 +1075,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             else if (genMask != 0u)
             {
                 // ---- G: the next frame of this lane's pixel ----
-                stallDebt += nStalled * (kFixedLight ? (ATX_WQ_GDUAL ? 2u * ATX_WQ_GPAIRS : ATX_WQ_GREPEAT) : 1u);
+                stallDebt += nStalled * (kFixedLight ? 2u * ATX_WQ_GPAIRS : 1u);
                 WQ_STAT(0, 1); WQ_STAT(1, __popc(genMask)); WQ_STAT(2, nStalled);
                 WQ_STAT(3, __popc(__ballot_sync(kFull, live && j >= p.nFrames)));
                 if (!kFixedLight)
@@ -1091,7 +1097,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     // path_bounce (Renderer.cu:371-384) at bounce 0 with the per-pixel constants folded in. The path
                     // state of this branch IS the per-pixel constants plus a seed and a direction, so it is kept in
                     // its own registers and queued from them (no copy into a PathState)
-#if ATX_WQ_GDUAL
                     // Two frames side by side in straight-line code: the three hashes, the sampler and the sphere tests
                     // of frame j and frame j + 1 are independent chains, so they fill each other's latencies (five warps
                     // per scheduler do not hide a serial PCG chain on their own). A lane whose path dies at the roulette
@@ -1232,97 +1237,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                         if (qCount > 32u)
                             break;
                     }
-#else
-#if ATX_WQ_GUNROLL == 1
-#pragma unroll
-#elif ATX_WQ_GUNROLL == 2
-#pragma unroll 2
-#else
-#pragma unroll 1
-#endif
-                    for (uint32_t rep = 0u; rep < ATX_WQ_GREPEAT; rep++)
-                    {
-                    // (several frames per pass: the pass overhead - ring consumption, ballots, the B decision - is
-                    // paid once; a further frame only while the queue is sure to take 32 more hits)
-                    const bool genNow = rep == 0u ? gen : (live && j < p.nFrames && (j - head) < K);
-                    bool hit = false;
-                    uint32_t seed = 0u;
-                    V3 nd = { 0.0f, 0.0f, 0.0f };
-                    const uint32_t gtag = lane | ((j & (K - 1u)) << 8);
-                    if (genNow)
-                    {
-                        rays += raysPerStart;
-                        seed = pixel * (p.firstFrame + j * p.frameStride);
-                        bool flying = false;
-                        if (!(pcg_float(seed) > pr0))
-                        {
-                            float lx, ly, lz;
-                            sample_local(ggx0, ggxT0, seed, lx, ly, lz);
-                            nd = frame_combine(N0, T0, B0, lx, ly, lz);
-                            if (1 < p.maxBounces)
-                            {
-                                seed += 1u; // Renderer.cu:306
-                                flying = true;
-                            }
-                        }
-                        if (flying)
-                        {
-                            if (kHoist)
-                            {
-                                hitT = 3.402823466e+38f; // FLT_MAX
-                                hitC = -1;
-                                const RayConst rk = ray_constants(nd.x, nd.y, nd.z);
-#pragma unroll
-                                for (int i = 0; i < kH; i++)
-                                    flat_tail(fdot3(hocx[i], hocy[i], hocz[i], nd.x, nd.y, nd.z), hcc[i], i, rk, hitT, hitC);
-                                traced++;
-                            }
-                            else
-                                trace_ray(o0x, o0y, o0z, nd.x, nd.y, nd.z, hitT, hitC);
-                            rays++;
-                            hit = hitC >= 0;
-                        }
-                        if (!hit)
-                        {
-                            // the path is complete: its sample is the cached color (+ the sky seen by the bounce ray,
-                            // path_miss); straight to the sum when nothing older is pending
-                            float cr = c0r, cg = c0g, cb = c0b;
-                            if (flying && p.skyLight)
-                            {
-                                cr = ffma(tq0x, 0.6f, cr);
-                                cg = ffma(tq0y, 0.7f, cg);
-                                cb = ffma(tq0z, 0.9f, cb);
-                            }
-                            if (head == j)
-                            {
-                                acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
-                                acc.w = fadd(acc.w, 1.0f);
-                                head++;
-                            }
-                            else
-                                complete3(gtag, cr, cg, cb);
-                        }
-                        j++;
-                    }
-                    const unsigned m = __ballot_sync(kFull, hit);
-                    if (hit)
-                    {
-                        const uint32_t e = (qHead + qCount + __popc(m & ((1u << lane) - 1u))) & (kQueueCap - 1u);
-                        qf[0u * kQueueCap + e] = o0x; qf[1u * kQueueCap + e] = o0y; qf[2u * kQueueCap + e] = o0z;
-                        qf[3u * kQueueCap + e] = nd.x; qf[4u * kQueueCap + e] = nd.y; qf[5u * kQueueCap + e] = nd.z;
-                        qf[6u * kQueueCap + e] = c0r; qf[7u * kQueueCap + e] = c0g; qf[8u * kQueueCap + e] = c0b;
-                        qf[9u * kQueueCap + e] = tq0x; qf[10u * kQueueCap + e] = tq0y; qf[11u * kQueueCap + e] = tq0z;
-                        q[12u * kQueueCap + e] = seed;
-                        q[13u * kQueueCap + e] = 1u; // bounce
-                        qf[14u * kQueueCap + e] = hitT;
-                        q[15u * kQueueCap + e] = static_cast<uint32_t>(hitC);
-                        q[16u * kQueueCap + e] = gtag;
-                    }
-                    qCount += __popc(m);
-                    if (qCount > 32u)
-                        break;
-                    }
-#endif
                 }
             }
             else if (__all_sync(kFull, exhausted && !live))

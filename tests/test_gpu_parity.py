@@ -259,6 +259,44 @@ def test_live_edge_scenes(atx, tmp_path):
     _live_compare(atx, p, 200, 100, 6, True, 2)
 
 
+@pytest.mark.parametrize("n_spheres", [1, 2, 3, 4, 5])
+def test_live_tiny_scenes_compiled_sphere_counts(atx, tmp_path, n_spheres):
+    """Scenes of 1..4 spheres run small-scene kernels with the sphere count compiled in (megakernel_ww<*, N>,
+    megakernel_wq<*, N>: straight-line sphere tests without the reference's branches and second root, and with one
+    light the origin-only part of a test hoisted per pixel); 5 spheres take the run-time count. Each directly
+    against the reference CUDA renderer, one light and two, few frames (while-while) and many (warp-queue, in
+    pairs of frames: odd and even frame counts, ring wrap-around)."""
+    for lights in (1, 2):
+        scene = atx.synthetic.small(n_spheres, lights, seed=40 + n_spheres)
+        p = tmp_path / f"tiny{n_spheres}_{lights}.json"
+        atx.Utils.exportScene(scene, str(p))
+        _live_compare(atx, p, 200, 112, 8, True, 2, expect_kind=atx.MEGA_WHILE_WHILE)
+        wq = atx.MEGA_WARP_QUEUE if lights == 1 else atx.MEGA_WHILE_WHILE
+        _live_compare(atx, p, 200, 112, 8, True, 37, expect_kind=wq)
+        _live_compare(atx, p, 200, 112, 8, lights == 2, 38, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE, one_launch=True)
+
+
+def test_live_degenerate_geometry(atx, tmp_path):
+    """Inputs at the edges of the branch-free sphere test (atx_device.cuh: flat_tail): the camera inside a sphere
+    (the reference reports no hit: min(t0, t1) < 0), concentric and overlapping spheres, a sphere of radius 0, a
+    tiny and a huge one, a sphere centred on the camera (b = 0), a light inside a sphere. Three spheres (compiled
+    count, hoisted origin part) and seven (run-time count), against the reference CUDA renderer."""
+    from ataraxia_b200.api import Sphere
+    for k, extra in enumerate([[((0.0, 3.0, 12.0), 2.5), ((0.0, 1.0, 0.0), 1.0)],
+                               [((0.0, 3.0, 12.0), 0.75), ((0.0, 1.0, 0.0), 1.0), ((0.0, 1.0, 0.0), 1.5), ((0.4, 1.2, 0.3), 1.0),
+                                ((2.0, 0.5, 1.0), 0.0), ((-2.0, 1e-3, 2.0), 1e-3)]]):
+        scene = atx.synthetic.small(1, 1, seed=77)           # the ground sphere + one light
+        for c, r in extra:
+            scene.rootNode.addSphere(Sphere(c, r, 3))
+        if k == 1:
+            scene.lights[0].position = (0.0, 1.0, 0.0)       # inside the concentric pair
+        p = tmp_path / f"degenerate{k}.json"
+        atx.Utils.exportScene(scene, str(p))
+        _live_compare(atx, p, 160, 96, 8, True, 3)
+        _live_compare(atx, p, 160, 96, 8, True, 40, kind=atx.MEGA_WARP_QUEUE, expect_kind=atx.MEGA_WARP_QUEUE, one_launch=True)
+        _live_compare(atx, p, 160, 96, 8, True, 5, kind=atx.MEGA_PAIR)
+
+
 # ---- CPU oracle port (always available): hit indices equal, radiance within tolerance ---------------
 def test_vs_cpu_oracle_port(atx, port):
     scene = atx.Utils.importScene(str(GOLDEN / "sample_scene.json"))
