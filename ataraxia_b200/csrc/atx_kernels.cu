@@ -834,7 +834,10 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     stage_spheres(sphS, p.spheres, p.nSpheres);
     __syncthreads();
 
-    uint32_t rays = 0, traced = 0, paths = 0;
+    // `traced` counts sphere loops that ran. Every one of them in this kernel stands for one traceRay call of the reference;
+    // the calls it does NOT run (the per-frame primary ray, the cached first shadow ray) are a per-pixel constant times
+    // the frames of the pixel and are added once per pixel (raysFixed): rays = traced + raysFixed
+    uint32_t raysFixed = 0, traced = 0, paths = 0;
 #ifdef ATX_WQ_STATS
     unsigned long long wqStat[8] = {};
 #endif
@@ -865,7 +868,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     V3 d0 = { 0.0f, 0.0f, 0.0f };
     float tPrimary = 0.0f;
     int cPrimary = -1;
-    uint32_t raysPerStart = 1;
     float c0r = 0.0f, c0g = 0.0f, c0b = 0.0f, o0x = 0.0f, o0y = 0.0f, o0z = 0.0f;
     V3 N0 = { 0.0f, 0.0f, 0.0f }, T0 = { 0.0f, 0.0f, 0.0f }, B0 = { 0.0f, 0.0f, 0.0f };
     float pr0 = 0.0f, tq0x = 0.0f, tq0y = 0.0f, tq0z = 0.0f, ggxT0 = 0.0f;
@@ -905,7 +907,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             if (cPrimary < 0)
             {
                 accumulate_sky(p, acc, p.nFrames);
-                rays += p.nFrames;
+                raysFixed += p.nFrames;
                 store = true;
             }
             else
@@ -914,7 +916,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 tPrimary = q0.x; pr0 = q0.z; ggxT0 = q0.w;
                 c0r = q1.x; c0g = q1.y; c0b = q1.z;
                 const uint32_t flags = __float_as_uint(q1.w);
-                raysPerStart = flags & 0xffu;
                 ggx0 = (flags >> 8) != 0u;
                 o0x = q2.x; o0y = q2.y; o0z = q2.z; tq0x = q2.w;
                 N0 = { q3.x, q3.y, q3.z }; tq0y = q3.w;
@@ -944,10 +945,11 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             PathState s;
             path_begin(s, p.cam.pos, d0, pixel, p.firstFrame);
             trace(s, tPrimary, cPrimary);
+            raysFixed -= 1u; // (this sphere loop is the first of the nFrames primary calls counted for the pixel)
             if (cPrimary < 0)
             {
                 accumulate_sky(p, acc, p.nFrames);
-                rays += p.nFrames;
+                raysFixed += p.nFrames;
                 store = true;
             }
             else
@@ -955,7 +957,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 live = true;
                 j = 0u;
                 head = 0u;
-                raysPerStart = 1u;
             }
         }
         if (store)
@@ -997,6 +998,8 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 if (p.emitRgba)
                     p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
                 paths += p.nFrames;
+                // reference calls per frame that the cached start stands for: the primary ray, and with one light the first shadow ray
+                raysFixed += p.nFrames * (kFixedLight ? (__float_as_uint(p.pixelCache[static_cast<size_t>(pixel) * kPrologueStride + 1].w) & 0xffu) : 1u);
                 live = false;
             }
             {
@@ -1050,14 +1053,12 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                         float tmin;
                         int closest;
                         trace(s, tmin, closest);
-                        rays++;
                         path_shadow(p, s, closest, tmin);
                     }
                     bool ended = path_bounce(p, s);
                     if (!ended)
                     {
                         trace(s, hitT, hitC);
-                        rays++;
                         if (hitC >= 0)
                             wantPush = true;
                         else
@@ -1084,7 +1085,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     {
                         // the path starts at the cached primary hit: straight to the bounce queue
                         tag = lane | ((j & (K - 1u)) << 8);
-                        rays += raysPerStart;
                         path_begin(s, p.cam.pos, d0, pixel, p.firstFrame + j * p.frameStride);
                         wantPush = true;
                         hitT = tPrimary;
@@ -1158,10 +1158,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                         }
                         const unsigned m2 = __ballot_sync(kFull, hitA && hitB);
                         const uint32_t tagA = lane | ((j & (K - 1u)) << 8), tagB = lane | (((j + 1u) & (K - 1u)) << 8);
-                        if (onA)
-                            rays += raysPerStart + (flyA ? 1u : 0u);
-                        if (onB)
-                            rays += raysPerStart + (flyB ? 1u : 0u);
                         if (kHoist)
                             traced += (flyA ? 1u : 0u) + (flyB ? 1u : 0u);
                         // samples that are complete, in frame order: the cached color (+ the sky seen by the bounce ray,
@@ -1270,7 +1266,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
         for (int i = 0; i < 8; i++)
             atomicAdd(&g_wqStats[i], wqStat[i]);
 #endif
-    count_rays(p, rays, traced, paths);
+    count_rays(p, traced + raysFixed, traced, paths);
 }
 
 // ---------------------------------------------------------------------------
