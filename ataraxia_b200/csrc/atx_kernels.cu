@@ -831,13 +831,18 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     uint32_t* q = done + 32u;                            // [kQueueFields][kQueueCap]
     float* qf = reinterpret_cast<float*>(q);
 
+    unsigned long long* ctaCount = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint32_t*>(smem + round_up8(p.nSpheres)) + kWqWarps * kWqWordsPerWarp); // [0] paths, [1] raysFixed
+    if (threadIdx.x < 2u)
+        ctaCount[threadIdx.x] = 0ull;
     stage_spheres(sphS, p.spheres, p.nSpheres);
     __syncthreads();
 
     // `traced` counts sphere loops that ran. Every one of them in this kernel stands for one traceRay call of the reference;
     // the calls it does NOT run (the per-frame primary ray, the cached first shadow ray) are a per-pixel constant times
     // the frames of the pixel and are added once per pixel (raysFixed): rays = traced + raysFixed
-    uint32_t raysFixed = 0, traced = 0, paths = 0;
+    // (raysFixed and the path count change once per pixel: two CTA-wide words in shared memory instead of two registers
+    // per lane - this kernel has no register to spare)
+    uint32_t traced = 0;
 #ifdef ATX_WQ_STATS
     unsigned long long wqStat[8] = {};
 #endif
@@ -864,6 +869,9 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
     bool live = false;      // owns a pixel with frames to render through G/B
     bool exhausted = false; // the pool has no more pixels
     uint32_t pixel = 0, j = 0, head = 0; // frames started / frames added to the sum
+    // running sums of the pixel. The sample count (.w) is not carried: it grows by exactly 1.0 per frame, so at retire it
+    // is the stored count + nFrames - formed in one addition where every intermediate count is an integer below 2^24 (the
+    // additions are then exact, one by one or at once), one by one otherwise
     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     V3 d0 = { 0.0f, 0.0f, 0.0f };
     float tPrimary = 0.0f;
@@ -907,7 +915,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             if (cPrimary < 0)
             {
                 accumulate_sky(p, acc, p.nFrames);
-                raysFixed += p.nFrames;
+                atomicAdd(ctaCount + 1, static_cast<unsigned long long>(p.nFrames));
                 store = true;
             }
             else
@@ -945,11 +953,11 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             PathState s;
             path_begin(s, p.cam.pos, d0, pixel, p.firstFrame);
             trace(s, tPrimary, cPrimary);
-            raysFixed -= 1u; // (this sphere loop is the first of the nFrames primary calls counted for the pixel)
+            atomicAdd(ctaCount + 1, ~0ull); // (this sphere loop is the first of the nFrames primary calls counted for the pixel)
             if (cPrimary < 0)
             {
                 accumulate_sky(p, acc, p.nFrames);
-                raysFixed += p.nFrames;
+                atomicAdd(ctaCount + 1, static_cast<unsigned long long>(p.nFrames));
                 store = true;
             }
             else
@@ -964,7 +972,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             store_pixel(p, pixel, acc);
             if (p.emitRgba)
                 p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
-            paths += p.nFrames;
+            atomicAdd(ctaCount, static_cast<unsigned long long>(p.nFrames));
         }
     };
 
@@ -981,7 +989,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                     acc.x = fadd(ring[(0u * K + slot) * 32u + lane], acc.x);
                     acc.y = fadd(ring[(1u * K + slot) * 32u + lane], acc.y);
                     acc.z = fadd(ring[(2u * K + slot) * 32u + lane], acc.z);
-                    acc.w = fadd(acc.w, 1.0f);
                     d &= ~(1u << slot);
                     head++;
                 }
@@ -994,12 +1001,22 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             if (live && head >= p.nFrames)
             {
                 // every frame of the pixel is in the sum: st.global.v4.f32 + the display pack
+                {
+                    float w = p.zeroFirst ? 0.0f : p.accum[pixel].w;
+                    const float n = u32_to_f32_rn(p.nFrames);
+                    if (w >= 0.0f && w == floorf(w) && p.nFrames <= 16777216u && w + n <= 16777216.0f)
+                        w = fadd(w, n);
+                    else
+                        for (uint32_t q = 0; q < p.nFrames; q++)
+                            w = fadd(w, 1.0f);
+                    acc.w = w;
+                }
                 store_pixel(p, pixel, acc);
                 if (p.emitRgba)
                     p.rgba[pixel] = pack_rgba8(acc, u32_to_f32_rn(p.rgbaDivisor));
-                paths += p.nFrames;
+                atomicAdd(ctaCount, static_cast<unsigned long long>(p.nFrames));
                 // reference calls per frame that the cached start stands for: the primary ray, and with one light the first shadow ray
-                raysFixed += p.nFrames * (kFixedLight ? (__float_as_uint(p.pixelCache[static_cast<size_t>(pixel) * kPrologueStride + 1].w) & 0xffu) : 1u);
+                atomicAdd(ctaCount + 1, static_cast<unsigned long long>(p.nFrames) * (kFixedLight ? (__float_as_uint(p.pixelCache[static_cast<size_t>(pixel) * kPrologueStride + 1].w) & 0xffu) : 1u));
                 live = false;
             }
             {
@@ -1174,7 +1191,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                             if (head == j)
                             {
                                 acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
-                                acc.w = fadd(acc.w, 1.0f);
                                 head++;
                             }
                             else
@@ -1192,7 +1208,6 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                             if (head == j + 1u)
                             {
                                 acc.x = fadd(cr, acc.x); acc.y = fadd(cg, acc.y); acc.z = fadd(cb, acc.z);
-                                acc.w = fadd(acc.w, 1.0f);
                                 head++;
                             }
                             else
@@ -1266,7 +1281,13 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
         for (int i = 0; i < 8; i++)
             atomicAdd(&g_wqStats[i], wqStat[i]);
 #endif
-    count_rays(p, traced + raysFixed, traced, paths);
+    count_rays(p, traced, traced, 0u);
+    __syncthreads();
+    if (threadIdx.x == 0u && p.counters)
+    {
+        atomicAdd(p.counters + 0, ctaCount[0]);
+        atomicAdd(p.counters + 1, ctaCount[1]); // (sums modulo 2^64: the -1 of a primary loop and the +nFrames of its pixel always meet in the same CTA)
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1837,7 +1858,8 @@ int mega_kind(const RenderParams& p, int requested)
 
 static size_t warp_queue_smem_bytes(const RenderParams& p)
 {
-    return sizeof(float4) * ((static_cast<size_t>(p.nSpheres) + 7u) & ~size_t(7)) + sizeof(uint32_t) * kWqWordsPerWarp * kWqWarps;
+    // spheres + ring, done bits and hit queue per warp + two CTA-wide counters
+    return sizeof(float4) * ((static_cast<size_t>(p.nSpheres) + 7u) & ~size_t(7)) + sizeof(uint32_t) * (kWqWordsPerWarp * kWqWarps + 4u);
 }
 
 size_t megakernel_smem_bytes(const RenderParams& p)
