@@ -1042,6 +1042,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
 
             PathState s;
             bool wantPush = false;
+            bool bouncePass = false; // (with one light G queues its hits itself: only a bounce pass reaches the common push below)
             float hitT = 0.0f;
             int hitC = -1;
             uint32_t tag = 0u;
@@ -1053,6 +1054,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
             if (qCount != 0u && (genMask == 0u || stallDebt + 2u * qCount >= 2u * ATX_WQ_BFULL))
             {
                 stallDebt = 0u;
+                bouncePass = true;
                 WQ_STAT(4, 1); WQ_STAT(5, qCount < 32u ? qCount : 32u);
                 // ---- B: one bounce for up to 32 queued hits ----
                 const uint32_t n = qCount < 32u ? qCount : 32u;
@@ -1259,6 +1261,8 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 continue; // pixels were just retired or claimed: look again
 
             // ---- push the rays that hit (converged: every lane takes part in the ballot) ----
+            if (!kFixedLight || bouncePass)
+            {
             __syncwarp();
             const unsigned pushMask = __ballot_sync(kFull, wantPush);
             if (wantPush)
@@ -1275,6 +1279,7 @@ __global__ void __launch_bounds__(kWqWarps * 32, ATX_WQ_CTAS) megakernel_wq(cons
                 q[16u * kQueueCap + e] = tag;
             }
             qCount += __popc(pushMask);
+            }
             __syncwarp();
         }
 
