@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 // Same path_* code between traces as every other form, same frame order of the sums: the
 // results are bit-identical.
 //
-// Round 2, 22.6 -> 16.7 ms on config 2 (all bit-identical to the reference's 1024 frames):
+// Round 2, 22.6 -> 16.5 ms on config 2 (all bit-identical to the reference's 1024 frames):
 //  * sphere tests as the reference's sequence without its branches and without its second root
 //    (flat_tail, atx_device.cuh), sphere count compiled in for scenes of up to 4 spheres (kN): the
 //    tests of a ray are straight-line code and interleave (-> 20.6 ms);
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(256, 3) megakernel_ww(const RenderParams p)
 //    is paid once per four frames, and a lane's first hit of a pair costs one push (-> 17.3 ms);
 //  * less per-lane state (ptxas asks for 109 registers, five CTAs per SM allow 96): the reference's ray
 //    count is derived from the traced count, the sample count is formed at retire, the per-pixel
-//    counters live in shared memory (-> 16.7 ms).
+//    counters live in shared memory, no common push after one-light G passes (-> 16.5 ms).
 // Measured and not kept: a 32-frame window with two-bit codes for samples that end without a
 // queued hit (fewer ring stalls - 29.2 lanes generating instead of 28.3 - but every sample then
 // goes through the summing loop: 19.3 ms); the bounce pass tracing its shadow ray and its
